@@ -1,0 +1,243 @@
+"""ctypes binding of include/iftwt.h — the Python mirror of the C ABI.
+
+The product is libiftwt.so (hand-written sm_100a CUDA behind a C ABI); this module
+only marshals numpy arrays across that boundary for the test-suite and bench.py.
+There is no CPU path here: if the library cannot be loaded or no B200 is visible,
+every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _build
+
+IFTWT_MAX_COST = 500
+
+STAGES = ("upload", "grid", "knn", "graph", "normals", "seeds", "ift", "download")
+
+
+class IftwtError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"iftwt error {code}: {msg}")
+        self.code = code
+
+
+class RgParams(C.Structure):
+    """pcl::RegionGrowing setters of main.cpp:111-119 (defaults are the reference's)."""
+    _fields_ = [("min_cluster_size", C.c_int), ("max_cluster_size", C.c_int),
+                ("number_of_neighbours", C.c_int), ("smoothness_threshold", C.c_float),
+                ("curvature_threshold", C.c_float)]
+
+    def __init__(self, min_cluster_size=50, max_cluster_size=10000, number_of_neighbours=50,
+                 smoothness_threshold=3.0 / 180.0 * np.pi, curvature_threshold=1.0):
+        super().__init__(min_cluster_size, max_cluster_size, number_of_neighbours,
+                         smoothness_threshold, curvature_threshold)
+
+
+class SegmentParams(C.Structure):
+    _fields_ = [("k_graph", C.c_int), ("k_normals", C.c_int), ("rg", RgParams), ("weights", C.c_int)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_points", C.c_uint64), ("n_cells", C.c_uint64), ("cell_size", C.c_double),
+                ("knn_fallback", C.c_uint64), ("n_arcs", C.c_uint64), ("rg_segments", C.c_uint64),
+                ("rg_sweeps", C.c_uint64), ("n_seeds", C.c_uint64), ("ift_levels", C.c_uint64),
+                ("kernel_launches", C.c_uint64), ("device_bytes", C.c_uint64)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+_lib = None
+
+
+def library_path() -> str:
+    return _build.LIB
+
+
+def load_library(build_if_missing: bool = True):
+    """Loads libiftwt.so; fails loudly (no fallback) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path):
+        if not build_if_missing:
+            raise ImportError(f"{path} is missing: run `python -m iftwt_rg_b200._build`")
+        _build.build()
+    lib = C.CDLL(path)
+    vp, sz, i32, f32 = C.c_void_p, C.c_size_t, C.c_int, C.c_float
+    lib.iftwt_version.restype = i32
+    lib.iftwt_last_error.restype = C.c_char_p
+    lib.iftwt_last_error.argtypes = [vp]
+    lib.iftwt_create.argtypes = [C.POINTER(vp), i32]
+    lib.iftwt_destroy.argtypes = [vp]
+    lib.iftwt_destroy.restype = None
+    lib.iftwt_set_cloud.argtypes = [vp, vp, sz, sz, i32, i32]
+    lib.iftwt_set_cloud_device.argtypes = [vp, vp, sz]
+    lib.iftwt_knn.argtypes = [vp, i32, vp, vp]
+    lib.iftwt_knn_query.argtypes = [vp, vp, sz, sz, i32, vp, vp]
+    lib.iftwt_knn_graph.argtypes = [vp, i32, vp, vp, sz, C.POINTER(sz)]
+    lib.iftwt_normals.argtypes = [vp, i32, vp, sz, i32, i32]
+    lib.iftwt_region_seeds.argtypes = [vp, C.POINTER(RgParams), vp, vp, sz, C.POINTER(sz)]
+    lib.iftwt_ift.argtypes = [vp, vp, vp, sz, vp, vp]
+    lib.iftwt_segment.argtypes = [vp, C.POINTER(SegmentParams), vp, vp, C.POINTER(sz)]
+    lib.iftwt_stage_ms.argtypes = [vp, i32, C.POINTER(f32)]
+    lib.iftwt_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.iftwt_reset_counters.argtypes = [vp]
+    lib.iftwt_synchronize.argtypes = [vp]
+    lib.iftwt_stream.argtypes = [vp]
+    lib.iftwt_stream.restype = vp
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One ctx = one GPU, one stream (include/iftwt.h)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load_library()
+        h = C.c_void_p()
+        rc = self._lib.iftwt_create(C.byref(h), device)
+        if rc != 0:
+            raise IftwtError(rc, self._lib.iftwt_last_error(None).decode())
+        self._h = h
+        self.n = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.iftwt_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise IftwtError(rc, self._lib.iftwt_last_error(self._h).decode())
+
+    # -- input ---------------------------------------------------------------
+    def set_cloud(self, pts: np.ndarray, xyz_offset: int = 0, intensity_offset: int | None = None):
+        """pts: (n, m) float32 rows (m >= 3) or a structured / byte array with explicit offsets."""
+        assert pts.flags.c_contiguous
+        n = pts.shape[0]
+        stride = pts.strides[0]
+        if intensity_offset is None:
+            intensity_offset = 12 if stride >= 16 else -1
+        self._keep = pts
+        self._check(self._lib.iftwt_set_cloud(self._h, _ptr(pts), stride, n, xyz_offset, intensity_offset))
+        self.n = n
+
+    def set_cloud_device(self, device_ptr: int, n: int):
+        self._check(self._lib.iftwt_set_cloud_device(self._h, C.c_void_p(device_ptr), n))
+        self.n = n
+
+    # -- stages --------------------------------------------------------------
+    def knn(self, k: int, want_d2: bool = True, download: bool = True):
+        if not download:
+            self._check(self._lib.iftwt_knn(self._h, k, None, None))
+            return None, None
+        idx = np.empty((self.n, k), np.int32)
+        d2 = np.empty((self.n, k), np.float32) if want_d2 else None
+        self._check(self._lib.iftwt_knn(self._h, k, _ptr(idx), _ptr(d2)))
+        return idx, d2
+
+    def knn_query(self, q: np.ndarray, k: int):
+        q = np.ascontiguousarray(q, np.float32)
+        m = q.shape[0]
+        idx = np.empty((m, k), np.int32)
+        d2 = np.empty((m, k), np.float32)
+        self._check(self._lib.iftwt_knn_query(self._h, _ptr(q), q.strides[0], m, k, _ptr(idx), _ptr(d2)))
+        return idx, d2
+
+    def knn_graph(self, k: int, download: bool = True):
+        narcs = C.c_size_t(0)
+        if not download:
+            self._check(self._lib.iftwt_knn_graph(self._h, k, None, None, 0, C.byref(narcs)))
+            return None, None
+        self._check(self._lib.iftwt_knn_graph(self._h, k, None, None, 0, C.byref(narcs)))
+        off = np.empty(self.n + 1, np.uint32)
+        adj = np.empty(narcs.value, np.uint32)
+        self._check(self._lib.iftwt_knn_graph(self._h, k, _ptr(off), _ptr(adj), adj.shape[0], C.byref(narcs)))
+        return off, adj
+
+    def normals(self, k: int, download: bool = True):
+        if not download:
+            self._check(self._lib.iftwt_normals(self._h, k, None, 16, 0, 12))
+            return None
+        out = np.empty((self.n, 4), np.float32)
+        self._check(self._lib.iftwt_normals(self._h, k, _ptr(out), 16, 0, 12))
+        return out
+
+    def region_seeds(self, params: RgParams | None = None, download: bool = True):
+        params = params or RgParams()
+        ns = C.c_size_t(0)
+        if not download:
+            self._check(self._lib.iftwt_region_seeds(self._h, C.byref(params), None, None, 0, C.byref(ns)))
+            return None, None
+        lab = np.empty(self.n, np.int32)
+        self._check(self._lib.iftwt_region_seeds(self._h, C.byref(params), _ptr(lab), None, 0, C.byref(ns)))
+        seeds = np.empty(ns.value, np.int32)
+        if ns.value:
+            self._check(self._lib.iftwt_region_seeds(self._h, C.byref(params), None, _ptr(seeds), ns.value,
+                                                     C.byref(ns)))
+        return lab, seeds
+
+    def ift(self, weights: np.ndarray | None = None, seeds: np.ndarray | None = None, download: bool = True):
+        w = None if weights is None else np.ascontiguousarray(weights, np.float32)
+        s = None if seeds is None else np.ascontiguousarray(seeds, np.int32)
+        cost = np.empty(self.n, np.uint32) if download else None
+        label = np.empty(self.n, np.uint32) if download else None
+        self._check(self._lib.iftwt_ift(self._h, _ptr(w), _ptr(s), 0 if s is None else s.shape[0], _ptr(cost),
+                                        _ptr(label)))
+        return cost, label
+
+    def segment(self, k_graph: int, k_normals: int | None = None, rg: RgParams | None = None,
+                cost: np.ndarray | None = None, label: np.ndarray | None = None, download: bool = True):
+        """main.cpp:97-123 in one call."""
+        p = SegmentParams(k_graph, k_normals or k_graph, rg or RgParams(number_of_neighbours=k_graph), 0)
+        ns = C.c_size_t(0)
+        if download:
+            cost = np.empty(self.n, np.uint32) if cost is None else cost
+            label = np.empty(self.n, np.uint32) if label is None else label
+        self._check(self._lib.iftwt_segment(self._h, C.byref(p), _ptr(cost), _ptr(label), C.byref(ns)))
+        return cost, label, ns.value
+
+    # -- instrumentation -----------------------------------------------------
+    def stage_ms(self) -> dict:
+        out = {}
+        v = C.c_float(0)
+        for i, name in enumerate(STAGES):
+            self._check(self._lib.iftwt_stage_ms(self._h, i, C.byref(v)))
+            out[name] = float(v.value)
+        return out
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._check(self._lib.iftwt_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def reset_counters(self):
+        self._check(self._lib.iftwt_reset_counters(self._h))
+
+    def synchronize(self):
+        self._check(self._lib.iftwt_synchronize(self._h))
+
+    def stream(self) -> int:
+        return int(self._lib.iftwt_stream(self._h) or 0)

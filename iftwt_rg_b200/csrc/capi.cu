@@ -1,0 +1,409 @@
+// capi.cu — the extern "C" boundary declared in include/iftwt.h.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "common.cuh"
+
+#define SID_NONE 0xFFFFFFFFu
+
+static thread_local std::string g_err;  // for failures before a ctx exists
+
+namespace {
+
+// strided host records -> packed float4 {x,y,z,intensity}
+__global__ void repack_kernel(const unsigned char* __restrict__ raw, size_t stride, u32 n, int xyz_off, int i_off,
+                              float4* __restrict__ out) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned char* r = raw + (size_t)i * stride;
+  const float* xyz = (const float*)(r + xyz_off);
+  float w = i_off >= 0 ? *(const float*)(r + i_off) : 0.f;
+  out[i] = make_float4(xyz[0], xyz[1], xyz[2], w);
+}
+__global__ void pack_queries_kernel(const unsigned char* __restrict__ raw, size_t stride, u32 m,
+                                    float4* __restrict__ out) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const float* xyz = (const float*)(raw + (size_t)i * stride);
+  out[i] = make_float4(xyz[0], xyz[1], xyz[2], 0.f);
+}
+// k-NN rows: sorted space -> original space
+__global__ void export_knn_kernel(const u32* __restrict__ nbr, const float* __restrict__ nd2,
+                                  const u32* __restrict__ inv, const u32* __restrict__ perm, size_t n_entries,
+                                  int k, int* __restrict__ idx_o, float* __restrict__ d2_o) {
+  size_t a = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_entries) return;
+  u32 i = (u32)(a / k);
+  int j = (int)(a - (size_t)i * k);
+  size_t src = (size_t)inv[i] * k + j;
+  u32 s = nbr[src];
+  idx_o[a] = s == SID_NONE ? -1 : (int)perm[s];
+  if (d2_o) d2_o[a] = nd2[src];
+}
+__global__ void export_query_kernel(const u32* __restrict__ sid, const u32* __restrict__ perm, size_t n_entries,
+                                    int* __restrict__ idx_o) {
+  size_t a = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_entries) return;
+  u32 s = sid[a];
+  idx_o[a] = s == SID_NONE ? -1 : (int)perm[s];
+}
+__global__ void export_normals_kernel(const float4* __restrict__ nrm, const u32* __restrict__ inv, u32 n,
+                                      float4* __restrict__ out) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = nrm[inv[i]];
+}
+
+int check_ctx(iftwt_ctx* c) {
+  if (!c) {
+    g_err = "null ctx";
+    return IFTWT_ERR_INVALID;
+  }
+  cudaError_t e = cudaSetDevice(c->device);
+  if (e != cudaSuccess) return ctx_fail(c, IFTWT_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  return IFTWT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int iftwt_version(void) { return IFTWT_VERSION; }
+
+const char* iftwt_last_error(const iftwt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+int iftwt_create(iftwt_ctx** out, int device) {
+  if (!out) {
+    g_err = "null out pointer";
+    return IFTWT_ERR_INVALID;
+  }
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_err = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (there is no CPU fallback)";
+    return IFTWT_ERR_CUDA;
+  }
+  if (device < 0 || device >= count) {
+    g_err = "device ordinal out of range";
+    return IFTWT_ERR_INVALID;
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    g_err = cudaGetErrorString(e);
+    return IFTWT_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    char b[160];
+    snprintf(b, sizeof b, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major,
+             prop.minor);
+    g_err = b;
+    return IFTWT_ERR_CUDA;
+  }
+  iftwt_ctx* c = new (std::nothrow) iftwt_ctx();
+  if (!c) {
+    g_err = "out of host memory";
+    return IFTWT_ERR_CUDA;
+  }
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMallocHost(&c->h_scalars, 4096) != cudaSuccess) {
+    g_err = std::string("ctx setup failed: ") + cudaGetErrorString(cudaGetLastError());
+    delete c;
+    return IFTWT_ERR_CUDA;
+  }
+  for (int s = 0; s < IFTWT_STAGE_COUNT; ++s) {
+    cudaEventCreate(&c->ev0[s]);
+    cudaEventCreate(&c->ev1[s]);
+    c->ev_set[s] = false;
+  }
+  memset(&c->stats, 0, sizeof c->stats);
+  *out = c;
+  return IFTWT_OK;
+}
+
+void iftwt_destroy(iftwt_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  DevBuf* bufs[] = {&c->pts_in, &c->stage_in, &c->spts, &c->perm, &c->inv, &c->keys, &c->keys_alt, &c->vals_alt,
+                    &c->tmp, &c->scalars, &c->cell_key, &c->cell_cnt, &c->cell_start, &c->hkeys, &c->hvals,
+                    &c->qb2, &c->nbr, &c->nd2, &c->kth, &c->fb_list, &c->g_off, &c->g_adj, &c->g_deg, &c->nrm,
+                    &c->rg_rank, &c->rg_parent, &c->rg_label, &c->rg_aux, &c->rg_aux2, &c->seeds, &c->ift_state,
+                    &c->ift_parent, &c->ift_w, &c->ift_byw, &c->ift_local, &c->out_a, &c->out_b};
+  for (DevBuf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  if (c->h_scalars) cudaFreeHost(c->h_scalars);
+  for (int s = 0; s < IFTWT_STAGE_COUNT; ++s) {
+    cudaEventDestroy(c->ev0[s]);
+    cudaEventDestroy(c->ev1[s]);
+  }
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+static void invalidate(iftwt_ctx* c) {
+  c->grid_valid = false;
+  c->grid_k = 0;
+  c->knn_k = 0;
+  c->graph_k = 0;
+  c->nrm_k = 0;
+  c->seeds_valid = false;
+  c->ift_valid = false;
+  c->n_seeds = 0;
+  c->n_arcs = 0;
+}
+
+int iftwt_set_cloud(iftwt_ctx* c, const void* points, size_t stride, size_t n, int xyz_off, int i_off) {
+  TRY(check_ctx(c));
+  if (!points || n == 0 || n >= 0x7FFFFFF0ull || stride < 12 || xyz_off < 0 || (size_t)xyz_off + 12 > stride ||
+      (i_off >= 0 && (size_t)i_off + 4 > stride) || (xyz_off & 3) || (i_off >= 0 && (i_off & 3)) || (stride & 3))
+    return ctx_fail(c, IFTWT_ERR_INVALID, "bad cloud description (n=%zu stride=%zu xyz_off=%d i_off=%d)", n,
+                    stride, xyz_off, i_off);
+  invalidate(c);
+  ENSURE(c, c->scalars, 4096);
+  ENSURE(c, c->pts_in, n * 16);
+  StageTimer st(c, IFTWT_STAGE_UPLOAD);
+  if (stride == 16 && xyz_off == 0 && i_off == 12) {
+    CU_TRY(c, cudaMemcpyAsync(c->pts_in.p, points, n * 16, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    ENSURE(c, c->stage_in, n * stride);
+    CU_TRY(c, cudaMemcpyAsync(c->stage_in.p, points, n * stride, cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, repack_kernel, div_up(n, 256), 256, 0, c->stage_in.as<unsigned char>(), stride, (u32)n, xyz_off,
+           i_off, c->pts_in.as<float4>());
+    CHECK_LAUNCH(c);
+  }
+  c->n = n;
+  c->stats.n_points = n;
+  return IFTWT_OK;
+}
+
+int iftwt_set_cloud_device(iftwt_ctx* c, const void* device_float4, size_t n) {
+  TRY(check_ctx(c));
+  if (!device_float4 || n == 0 || n >= 0x7FFFFFF0ull) return ctx_fail(c, IFTWT_ERR_INVALID, "bad device cloud");
+  invalidate(c);
+  ENSURE(c, c->scalars, 4096);
+  ENSURE(c, c->pts_in, n * 16);
+  StageTimer st(c, IFTWT_STAGE_UPLOAD);
+  CU_TRY(c, cudaMemcpyAsync(c->pts_in.p, device_float4, n * 16, cudaMemcpyDeviceToDevice, c->stream));
+  c->n = n;
+  c->stats.n_points = n;
+  return IFTWT_OK;
+}
+
+static void note_fallback(iftwt_ctx* c) { c->stats.knn_fallback = ((u32*)c->h_scalars)[48]; }
+
+int iftwt_knn(iftwt_ctx* c, int k, int32_t* idx, float* d2) {
+  TRY(check_ctx(c));
+  TRY(knn_run(c, k));
+  const size_t ne = c->n * (size_t)k;
+  if (idx) {
+    StageTimer st(c, IFTWT_STAGE_DOWNLOAD);
+    ENSURE(c, c->out_a, ne * 4);
+    if (d2) ENSURE(c, c->out_b, ne * 4);
+    LAUNCH(c, export_knn_kernel, div_up(ne, 256), 256, 0, c->nbr.as<u32>(), c->nd2.as<float>(), c->inv.as<u32>(),
+           c->perm.as<u32>(), ne, k, c->out_a.as<int>(), d2 ? c->out_b.as<float>() : (float*)nullptr);
+    CHECK_LAUNCH(c);
+    CU_TRY(c, cudaMemcpyAsync(idx, c->out_a.p, ne * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (d2) CU_TRY(c, cudaMemcpyAsync(d2, c->out_b.p, ne * 4, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  note_fallback(c);
+  return IFTWT_OK;
+}
+
+int iftwt_knn_query(iftwt_ctx* c, const void* queries, size_t stride, size_t m, int k, int32_t* idx, float* d2) {
+  TRY(check_ctx(c));
+  if (c->n == 0) return ctx_fail(c, IFTWT_ERR_STATE, "no cloud set");
+  if (!queries || stride < 12 || (stride & 3) || m >= 0x7FFFFFF0ull)
+    return ctx_fail(c, IFTWT_ERR_INVALID, "bad query description");
+  if (m == 0) return IFTWT_OK;
+  if (!c->grid_valid) TRY(grid_build(c, k < 8 ? 8 : k));
+  const size_t ne = m * (size_t)k;
+  ENSURE(c, c->stage_in, m * stride + m * 16 + 16);
+  unsigned char* raw = c->stage_in.as<unsigned char>() + ((m * 16 + 15) & ~(size_t)15);
+  float4* q4 = c->stage_in.as<float4>();
+  CU_TRY(c, cudaMemcpyAsync(raw, queries, m * stride, cudaMemcpyHostToDevice, c->stream));
+  LAUNCH(c, pack_queries_kernel, div_up(m, 256), 256, 0, raw, stride, (u32)m, q4);
+  ENSURE(c, c->out_a, ne * 4 * 2);
+  ENSURE(c, c->out_b, ne * 4);
+  u32* sid = c->out_a.as<u32>();
+  int* idx_o = (int*)(sid + ne);
+  TRY(knn_query_run(c, q4, m, k, sid, c->out_b.as<float>()));
+  LAUNCH(c, export_query_kernel, div_up(ne, 256), 256, 0, sid, c->perm.as<u32>(), ne, idx_o);
+  CHECK_LAUNCH(c);
+  if (idx) CU_TRY(c, cudaMemcpyAsync(idx, idx_o, ne * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (d2) CU_TRY(c, cudaMemcpyAsync(d2, c->out_b.p, ne * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return IFTWT_OK;
+}
+
+int iftwt_knn_graph(iftwt_ctx* c, int k, uint32_t* off, uint32_t* adj, size_t cap, size_t* n_arcs) {
+  TRY(check_ctx(c));
+  TRY(knn_run(c, k));
+  TRY(graph_build(c));
+  if (off || adj) {
+    TRY(graph_export(c, off, adj, cap, n_arcs));
+  } else {
+    if (n_arcs) *n_arcs = c->n_arcs;
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+  }
+  note_fallback(c);
+  return IFTWT_OK;
+}
+
+int iftwt_normals(iftwt_ctx* c, int k, void* out, size_t stride, int normal_off, int curv_off) {
+  TRY(check_ctx(c));
+  TRY(knn_run(c, k));
+  TRY(normals_run(c));
+  if (out) {
+    if (stride < 16 || normal_off < 0 || curv_off < 0 || (size_t)normal_off + 12 > stride ||
+        (size_t)curv_off + 4 > stride)
+      return ctx_fail(c, IFTWT_ERR_INVALID, "bad normal record description");
+    StageTimer st(c, IFTWT_STAGE_DOWNLOAD);
+    const u32 n = (u32)c->n;
+    ENSURE(c, c->out_a, (size_t)n * 16);
+    LAUNCH(c, export_normals_kernel, div_up(n, 256), 256, 0, c->nrm.as<float4>(), c->inv.as<u32>(), n,
+           c->out_a.as<float4>());
+    CHECK_LAUNCH(c);
+    if (stride == 16 && normal_off == 0 && curv_off == 12) {
+      CU_TRY(c, cudaMemcpyAsync(out, c->out_a.p, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+      // two strided copies: xyz (12 bytes) and curvature (4 bytes) per record
+      CU_TRY(c, cudaMemcpy2DAsync((char*)out + normal_off, stride, c->out_a.p, 16, 12, n, cudaMemcpyDeviceToHost,
+                                  c->stream));
+      CU_TRY(c, cudaMemcpy2DAsync((char*)out + curv_off, stride, (char*)c->out_a.p + 12, 16, 4, n,
+                                  cudaMemcpyDeviceToHost, c->stream));
+    }
+  }
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  note_fallback(c);
+  return IFTWT_OK;
+}
+
+int iftwt_region_seeds(iftwt_ctx* c, const iftwt_rg_params* p, int32_t* point_label, int32_t* seed_index,
+                       size_t seed_cap, size_t* n_seeds) {
+  TRY(check_ctx(c));
+  if (!p) return ctx_fail(c, IFTWT_ERR_INVALID, "null params");
+  TRY(seeds_run(c, p));
+  if (n_seeds) *n_seeds = c->n_seeds;
+  if (point_label)
+    CU_TRY(c, cudaMemcpyAsync(point_label, c->out_a.p, c->n * 4, cudaMemcpyDeviceToHost, c->stream));
+  int rc = IFTWT_OK;
+  if (seed_index) {
+    if (seed_cap < c->n_seeds)
+      rc = ctx_fail(c, IFTWT_ERR_CAPACITY, "seed buffer needs %zu entries, caller gave %zu", c->n_seeds, seed_cap);
+    else if (c->n_seeds)
+      CU_TRY(c, cudaMemcpyAsync(seed_index, c->seeds.p, c->n_seeds * 4, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return rc;
+}
+
+int iftwt_ift(iftwt_ctx* c, const float* weights, const int32_t* seeds, size_t n_seeds, uint32_t* cost,
+              uint32_t* label) {
+  TRY(check_ctx(c));
+  if (c->graph_k == 0) return ctx_fail(c, IFTWT_ERR_STATE, "graph is not built (call iftwt_knn_graph first)");
+  const size_t n = c->n;
+  const float* d_w = nullptr;
+  if (weights) {
+    ENSURE(c, c->out_b, n * 4);
+    CU_TRY(c, cudaMemcpyAsync(c->out_b.p, weights, n * 4, cudaMemcpyHostToDevice, c->stream));
+    d_w = c->out_b.as<float>();
+  }
+  const u32* d_seeds;
+  size_t ns;
+  if (seeds) {
+    ENSURE(c, c->seeds, (n_seeds + 1) * 4);
+    if (n_seeds)
+      CU_TRY(c, cudaMemcpyAsync(c->seeds.p, seeds, n_seeds * 4, cudaMemcpyHostToDevice, c->stream));
+    c->n_seeds = n_seeds;
+    c->seeds_valid = true;
+    d_seeds = c->seeds.as<u32>();
+    ns = n_seeds;
+  } else {
+    if (!c->seeds_valid) return ctx_fail(c, IFTWT_ERR_STATE, "no seeds on the device (call iftwt_region_seeds)");
+    d_seeds = c->seeds.as<u32>();
+    ns = c->n_seeds;
+  }
+  TRY(ift_run(c, d_w, d_seeds, ns));
+  {
+    StageTimer st(c, IFTWT_STAGE_DOWNLOAD);
+    if (cost) CU_TRY(c, cudaMemcpyAsync(cost, c->out_a.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (label)
+      CU_TRY(c, cudaMemcpyAsync(label, c->out_a.as<u32>() + n, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return IFTWT_OK;
+}
+
+int iftwt_segment(iftwt_ctx* c, const iftwt_segment_params* p, uint32_t* cost, uint32_t* label, size_t* n_seeds) {
+  TRY(check_ctx(c));
+  if (!p) return ctx_fail(c, IFTWT_ERR_INVALID, "null params");
+  if (c->n == 0) return ctx_fail(c, IFTWT_ERR_STATE, "no cloud set");
+  if (p->weights != 0) return ctx_fail(c, IFTWT_ERR_UNSUPPORTED, "gradient weights are not built yet");
+  int kmax = p->k_graph;
+  if (p->k_normals > kmax) kmax = p->k_normals;
+  if (p->rg.number_of_neighbours > kmax) kmax = p->rg.number_of_neighbours;
+  TRY(grid_build(c, kmax));
+  // graph first (its lists may be overwritten by the other neighbourhood sizes)
+  TRY(knn_run(c, p->k_graph));
+  TRY(graph_build(c));
+  TRY(knn_run(c, p->k_normals));
+  TRY(normals_run(c));
+  TRY(seeds_run(c, &p->rg));
+  if (n_seeds) *n_seeds = c->n_seeds;
+  TRY(ift_run(c, nullptr, c->seeds.as<u32>(), c->n_seeds));
+  const size_t n = c->n;
+  {
+    StageTimer st(c, IFTWT_STAGE_DOWNLOAD);
+    if (cost) CU_TRY(c, cudaMemcpyAsync(cost, c->out_a.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (label)
+      CU_TRY(c, cudaMemcpyAsync(label, c->out_a.as<u32>() + n, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  note_fallback(c);
+  return IFTWT_OK;
+}
+
+int iftwt_stage_ms(iftwt_ctx* c, int stage, float* ms) {
+  TRY(check_ctx(c));
+  if (stage < 0 || stage >= IFTWT_STAGE_COUNT || !ms) return ctx_fail(c, IFTWT_ERR_INVALID, "bad stage");
+  if (!c->ev_set[stage]) {
+    *ms = 0.f;
+    return IFTWT_OK;
+  }
+  CU_TRY(c, cudaEventSynchronize(c->ev1[stage]));
+  CU_TRY(c, cudaEventElapsedTime(ms, c->ev0[stage], c->ev1[stage]));
+  return IFTWT_OK;
+}
+
+int iftwt_get_stats(iftwt_ctx* c, iftwt_stats* out) {
+  TRY(check_ctx(c));
+  if (!out) return ctx_fail(c, IFTWT_ERR_INVALID, "null out");
+  *out = c->stats;
+  return IFTWT_OK;
+}
+
+int iftwt_reset_counters(iftwt_ctx* c) {
+  TRY(check_ctx(c));
+  c->stats.kernel_launches = 0;
+  for (int s = 0; s < IFTWT_STAGE_COUNT; ++s) c->ev_set[s] = false;
+  return IFTWT_OK;
+}
+
+int iftwt_synchronize(iftwt_ctx* c) {
+  TRY(check_ctx(c));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return IFTWT_OK;
+}
+
+void* iftwt_stream(iftwt_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+}  // extern "C"

@@ -1,0 +1,195 @@
+// common.cuh — context, device buffers, launch bookkeeping shared by every stage.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/iftwt.h"
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef int64_t i64;
+
+#define IFTWT_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+
+// Grow-only device buffer owned by a ctx.
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  template <typename T>
+  T* as() const { return (T*)p; }
+};
+
+// Uniform grid over the Morton-sorted cloud (device view, passed by value).
+struct GridView {
+  double ox, oy, oz;   // grid origin (bbox min)
+  double inv_cell;     // 1 / cell size
+  double cell;         // cell size
+  int dimx, dimy, dimz;
+  u32 n_points;
+  u32 n_cells;
+  const u64* cell_key;    // [n_cells] Morton key of each occupied cell, ascending
+  const u32* cell_start;  // [n_cells + 1] first sorted point of each cell
+  const u64* hkeys;       // open-addressing hash: cell key -> cell index
+  const u32* hvals;
+  u32 hmask;
+};
+
+struct iftwt_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int sm_count = 148;
+
+  // --- cloud ---
+  size_t n = 0;
+  DevBuf pts_in;   // float4 [n] original order {x,y,z,intensity}
+  DevBuf stage_in; // raw host records when the input is not packed float4
+  DevBuf spts;     // float4 [n] Morton order {x,y,z,bits(orig index)}
+  DevBuf perm;     // u32 [n] sorted -> orig
+  DevBuf inv;      // u32 [n] orig -> sorted
+  DevBuf keys, keys_alt, vals_alt;  // sort scratch
+  DevBuf tmp;      // CUB temp storage
+  DevBuf scalars;  // small device scratch (counters, bbox, histograms)
+  void* h_scalars = nullptr;  // pinned mirror
+
+  // --- grid ---
+  bool grid_valid = false;
+  int grid_k = 0;
+  GridView grid{};
+  DevBuf cell_key, cell_cnt, cell_start, hkeys, hvals;
+  DevBuf qb2;      // float [n] squared one-ring completeness bound per sorted point
+
+  // --- knn ---
+  int knn_k = 0;   // 0 = none
+  DevBuf nbr;      // u32 [n*k] sorted space
+  DevBuf nd2;      // float [n*k]
+  DevBuf kth;      // u64 [n] key of the k-th neighbour (d2 bits << 32 | orig idx)
+  DevBuf fb_list;  // u32 [n] fallback query list
+  // --- graph ---
+  int graph_k = 0;
+  size_t n_arcs = 0;
+  DevBuf g_off, g_adj, g_deg;
+  // --- normals ---
+  int nrm_k = 0;
+  DevBuf nrm;  // float4 [n] sorted space {nx,ny,nz,curv}
+  // --- seeds ---
+  DevBuf rg_rank, rg_parent, rg_label, rg_aux, rg_aux2;
+  DevBuf seeds;  // u32 [n_seeds] orig indices
+  size_t n_seeds = 0;
+  bool seeds_valid = false;
+  // --- ift ---
+  DevBuf ift_state, ift_parent, ift_w, ift_byw, ift_local;
+  bool ift_valid = false;
+  // --- export scratch ---
+  DevBuf out_a, out_b;
+
+  // --- instrumentation ---
+  cudaEvent_t ev0[IFTWT_STAGE_COUNT], ev1[IFTWT_STAGE_COUNT];
+  bool ev_set[IFTWT_STAGE_COUNT];
+  iftwt_stats stats{};
+};
+
+int ctx_fail(iftwt_ctx* c, int code, const char* fmt, ...);
+int dev_ensure(iftwt_ctx* c, DevBuf& b, size_t bytes);
+
+#define CU_TRY(ctx, expr)                                                             \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess)                                                            \
+      return ctx_fail((ctx), IFTWT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,          \
+                      cudaGetErrorString(_e), __FILE__, __LINE__);                    \
+  } while (0)
+#define TRY(expr)              \
+  do {                         \
+    int _r = (expr);           \
+    if (_r != IFTWT_OK) return _r; \
+  } while (0)
+#define ENSURE(ctx, buf, bytes) TRY(dev_ensure((ctx), (buf), (bytes)))
+
+// every kernel launch goes through this so gpu_launches is a count, not a guess
+#define LAUNCH(ctx, kernel, grid, block, smem, ...)                         \
+  do {                                                                      \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);        \
+    (ctx)->stats.kernel_launches++;                                         \
+  } while (0)
+#define CHECK_LAUNCH(ctx) CU_TRY(ctx, cudaGetLastError())
+
+struct StageTimer {
+  iftwt_ctx* c;
+  int s;
+  StageTimer(iftwt_ctx* c_, int s_) : c(c_), s(s_) { cudaEventRecord(c->ev0[s], c->stream); }
+  ~StageTimer() {
+    cudaEventRecord(c->ev1[s], c->stream);
+    c->ev_set[s] = true;
+  }
+};
+
+static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// ---- stage entry points (host side), one per .cu ----
+int grid_build(iftwt_ctx* c, int k);                                       // grid.cu
+int knn_run(iftwt_ctx* c, int k);                                          // knn.cu
+int knn_query_run(iftwt_ctx* c, const float4* d_q, size_t m, int k, u32* d_idx_sorted, float* d_d2);  // knn.cu
+int graph_build(iftwt_ctx* c);                                             // graph.cu
+int graph_export(iftwt_ctx* c, u32* h_off, u32* h_adj, size_t cap, size_t* n_arcs);
+int normals_run(iftwt_ctx* c);                                             // normals.cu
+int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p);                     // seeds.cu
+int ift_run(iftwt_ctx* c, const float* d_w_orig /*or null*/, const u32* d_seeds_orig, size_t ns);  // ift.cu
+
+// ---- device helpers ----
+#ifdef __CUDACC__
+__device__ __forceinline__ u64 morton_spread(u32 v) {  // 21 bits -> every third bit
+  u64 x = v & 0x1FFFFFull;
+  x = (x | x << 32) & 0x1F00000000FFFFull;
+  x = (x | x << 16) & 0x1F0000FF0000FFull;
+  x = (x | x << 8) & 0x100F00F00F00F00Full;
+  x = (x | x << 4) & 0x10C30C30C30C30C3ull;
+  x = (x | x << 2) & 0x1249249249249249ull;
+  return x;
+}
+__device__ __forceinline__ u32 morton_compact(u64 x) {
+  x &= 0x1249249249249249ull;
+  x = (x ^ (x >> 2)) & 0x10C30C30C30C30C3ull;
+  x = (x ^ (x >> 4)) & 0x100F00F00F00F00Full;
+  x = (x ^ (x >> 8)) & 0x1F0000FF0000FFull;
+  x = (x ^ (x >> 16)) & 0x1F00000000FFFFull;
+  x = (x ^ (x >> 32)) & 0x1FFFFFull;
+  return (u32)x;
+}
+// x is the most significant axis bit of every triple
+__device__ __forceinline__ u64 morton3(u32 x, u32 y, u32 z) {
+  return (morton_spread(x) << 2) | (morton_spread(y) << 1) | morton_spread(z);
+}
+__device__ __forceinline__ void demorton3(u64 k, u32& x, u32& y, u32& z) {
+  x = morton_compact(k >> 2);
+  y = morton_compact(k >> 1);
+  z = morton_compact(k);
+}
+__device__ __forceinline__ u32 hash64(u64 k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return (u32)k;
+}
+// returns cell index or 0xFFFFFFFF
+__device__ __forceinline__ u32 grid_lookup(const GridView& g, u64 key) {
+  u32 slot = hash64(key) & g.hmask;
+  while (true) {
+    u64 k = g.hkeys[slot];
+    if (k == key) return g.hvals[slot];
+    if (k == IFTWT_EMPTY_KEY) return 0xFFFFFFFFu;
+    slot = (slot + 1) & g.hmask;
+  }
+}
+// FLANN L2_Simple<float> accumulation order, no contraction (oracle: dist2()).
+__device__ __forceinline__ float dist2_exact(float qx, float qy, float qz, float px, float py, float pz) {
+  float dx = __fsub_rn(qx, px), dy = __fsub_rn(qy, py), dz = __fsub_rn(qz, pz);
+  float r = __fmul_rn(dx, dx);
+  r = __fadd_rn(r, __fmul_rn(dy, dy));
+  r = __fadd_rn(r, __fmul_rn(dz, dz));
+  return r;
+}
+#endif

@@ -1,0 +1,436 @@
+// knn.cu — K1 / K1': exact k-NN on the Morton-sorted uniform grid.
+//
+// Replaces pcl::search::KdTree::nearestKSearch as called at graph.hpp:245 (k=2),
+// main.cpp:108 (k=30, inside NormalEstimationOMP), main.cpp:115 (k=50, inside
+// RegionGrowing), graph.hpp:260-266 / flat_point.hpp:74 / ift.hpp:135 (k=1 with an
+// arbitrary query point).  Results are the exact k nearest neighbours in the
+// canonical (d2, original index) order; d2 is FLANN's L2_Simple<float>
+// accumulation (common.cuh: dist2_exact), bit for bit the oracle's.
+//
+// Fast path (knn_cell_kernel): one warp per occupied cell.  The warp looks the 27
+// cells of the 3x3x3 block up in the cell hash, stages their points in shared
+// memory with coalesced float4 loads, and then answers the cell's own queries one
+// by one: 32 lanes evaluate the staged candidates, a count-based threshold search
+// (ballot + popc, candidates ~ tau in 2-D) narrows them to at most CS survivors,
+// and the survivors are ranked against each other in shared memory — the rank IS
+// the output slot, so no sorting network and no shuffles are needed.  A query is
+// finished when its k-th distance is inside the block (per-point bound from
+// grid.cu); otherwise it is appended to the fallback list.
+//
+// General path (knn_general_kernel): one warp per query, for fallback queries and
+// for external query points.  Stage j scans the 3x3x3 block of super-cells of side
+// cell*2^j (contiguous Morton-prefix ranges of the sorted cloud, found by binary
+// search in the cell table), keeps the k best in a lane-distributed sorted list,
+// and stops when the k-th distance is inside the scanned block.
+#include "common.cuh"
+
+#define KNN_WARPS 8
+#define KNN_CAP 256  // staged candidates per warp (8 per lane)
+#define KEY_MAX 0xFFFFFFFFFFFFFFFFull
+#define SID_NONE 0xFFFFFFFFu
+
+__device__ __forceinline__ u64 make_key(float d2, u32 orig) {
+  return ((u64)__float_as_uint(d2) << 32) | (u64)orig;
+}
+
+template <int E>  // E = CS / 32 survivor slots per lane
+__global__ void __launch_bounds__(KNN_WARPS * 32)
+knn_cell_kernel(GridView g, const float4* __restrict__ spts, const float* __restrict__ qb2, int k,
+                float tau0, u32* __restrict__ nbr, float* __restrict__ nd2, u64* __restrict__ kth,
+                u32* __restrict__ fb_list, u32* __restrict__ fb_count) {
+  constexpr int CS = 32 * E;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* s_pts_all = (float4*)smem_raw;                                    // [W][CAP]
+  u64* s_key_all = (u64*)(s_pts_all + KNN_WARPS * KNN_CAP);                 // [W][CS]
+  u32* s_id_all = (u32*)(s_key_all + KNN_WARPS * CS);                       // [W][CAP]
+  u32* s_sid_all = s_id_all + KNN_WARPS * KNN_CAP;                          // [W][CS]
+  float* s_kd2_all = (float*)(s_sid_all + KNN_WARPS * CS);                  // [W]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const u32 ci = blockIdx.x * KNN_WARPS + warp;
+  if (ci >= g.n_cells) return;  // warps are independent: no block-level barrier below
+  float4* s_pts = s_pts_all + warp * KNN_CAP;
+  u32* s_id = s_id_all + warp * KNN_CAP;
+  u64* s_key = s_key_all + warp * CS;
+  u32* s_sid = s_sid_all + warp * CS;
+  float* s_kd2 = s_kd2_all + warp;
+  const unsigned FULL = 0xffffffffu;
+
+  // ---- the 27 cells of the block ----
+  u32 cx, cy, cz;
+  demorton3(g.cell_key[ci], cx, cy, cz);
+  u32 nstart = 0, ncnt = 0;
+  if (lane < 27) {
+    int x = (int)cx + (lane % 3) - 1, y = (int)cy + ((lane / 3) % 3) - 1, z = (int)cz + (lane / 9) - 1;
+    if (x >= 0 && x < g.dimx && y >= 0 && y < g.dimy && z >= 0 && z < g.dimz) {
+      u32 cidx = (lane == 13) ? ci : grid_lookup(g, morton3((u32)x, (u32)y, (u32)z));
+      if (cidx != 0xFFFFFFFFu) {
+        nstart = g.cell_start[cidx];
+        ncnt = g.cell_start[cidx + 1] - nstart;
+      }
+    }
+  }
+  u32 incl = ncnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    u32 t = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const u32 excl = incl - ncnt;
+  const int M = (int)__shfl_sync(FULL, incl, 31);
+  const u32 qs = __shfl_sync(FULL, nstart, 13), qn = __shfl_sync(FULL, ncnt, 13);
+  const u32 qoff = __shfl_sync(FULL, excl, 13);
+
+  if (M > KNN_CAP || M < k) {  // too crowded to stage, or not enough candidates: general path
+    u32 base = 0;
+    if (lane == 0) base = atomicAdd(fb_count, qn);
+    base = __shfl_sync(FULL, base, 0);
+    for (u32 t = lane; t < qn; t += 32) fb_list[base + t] = qs + t;
+    return;
+  }
+
+  // ---- stage the candidates (coalesced float4 loads) ----
+  for (int j = 0; j < 27; ++j) {
+    u32 cn = __shfl_sync(FULL, ncnt, j);
+    if (cn == 0) continue;
+    u32 s = __shfl_sync(FULL, nstart, j), o = __shfl_sync(FULL, excl, j);
+    for (u32 t = lane; t < cn; t += 32) {
+      s_pts[o + t] = spts[s + t];
+      s_id[o + t] = s + t;
+    }
+  }
+  __syncwarp();
+
+  const float target = fminf(1.4f * (float)k, 0.5f * (float)(k + CS));
+  const float tiny = tau0 * 1e-6f;
+  float tau = tau0;
+
+  for (u32 q = 0; q < qn; ++q) {
+    const float4 Q = s_pts[qoff + q];
+    const u32 qid = qs + q;
+    float d[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      int slot = lane + 32 * r;
+      if (slot < M) {
+        float4 P = s_pts[slot];
+        d[r] = dist2_exact(Q.x, Q.y, Q.z, P.x, P.y, P.z);
+      } else {
+        d[r] = INFINITY;
+      }
+    }
+    // ---- threshold search: k <= #{d < tau} <= CS ----
+    int cnt = M;
+    bool ok = true;
+    if (M <= CS) {
+      tau = INFINITY;
+    } else {
+      ok = false;
+      float lo = 0.f, hi = INFINITY, t = tau;
+      int clo = 0, chi = M;
+      for (int it = 0; it < 24; ++it) {
+        cnt = 0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) cnt += __popc(__ballot_sync(FULL, d[r] < t));
+        if (cnt < k) {
+          lo = t;
+          clo = cnt;
+        } else if (cnt > CS) {
+          hi = t;
+          chi = cnt;
+        } else {
+          ok = true;
+          break;
+        }
+        float nt;
+        if (hi == INFINITY) {
+          nt = t * fminf(4.f, fmaxf(1.3f, target / fmaxf((float)cnt, 1.f)));
+        } else {
+          nt = lo + (hi - lo) * ((target - (float)clo) / (float)(chi - clo));
+          if (!(nt > lo && nt < hi)) nt = 0.5f * (lo + hi);
+          if (!(nt > lo && nt < hi)) break;  // adjacent floats: a tie cluster larger than CS
+        }
+        t = nt;
+      }
+      tau = t;
+    }
+    bool done = false;
+    if (ok) {
+      // ---- compact the survivors into shared memory ----
+      int base = 0;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        bool p = d[r] < tau;
+        unsigned m = __ballot_sync(FULL, p);
+        if (p) {
+          int pos = base + __popc(m & ((1u << lane) - 1u));
+          int slot = lane + 32 * r;
+          s_key[pos] = make_key(d[r], __float_as_uint(s_pts[slot].w));
+          s_sid[pos] = s_id[slot];
+        }
+        base += __popc(m);
+      }
+      __syncwarp();
+      // ---- rank = output slot ----
+      u64 mk[E];
+      int rk[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        mk[e] = (lane + 32 * e < cnt) ? s_key[lane + 32 * e] : KEY_MAX;
+        rk[e] = 0;
+      }
+      for (int i = 0; i < cnt; ++i) {
+        u64 x = s_key[i];
+#pragma unroll
+        for (int e = 0; e < E; ++e) rk[e] += (x < mk[e]) ? 1 : 0;
+      }
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        if (lane + 32 * e < cnt && rk[e] < k) {
+          nbr[(size_t)qid * k + rk[e]] = s_sid[lane + 32 * e];
+          nd2[(size_t)qid * k + rk[e]] = __uint_as_float((u32)(mk[e] >> 32));
+          if (rk[e] == k - 1) {
+            kth[qid] = mk[e];
+            *s_kd2 = __uint_as_float((u32)(mk[e] >> 32));
+          }
+        }
+      }
+      __syncwarp();
+      float kd2 = *s_kd2;
+      done = kd2 <= qb2[qid];
+      tau = fmaxf(kd2 * 1.4f, tiny);
+      __syncwarp();
+    } else {
+      tau = tau0;
+    }
+    if (!done && lane == 0) fb_list[atomicAdd(fb_count, 1u)] = qid;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// lane-distributed sorted list, position p = r*32 + lane, ascending keys
+template <int RL>
+struct WarpTopK {
+  u64 key[RL];
+  u32 sid[RL];
+  __device__ __forceinline__ void reset() {
+#pragma unroll
+    for (int r = 0; r < RL; ++r) {
+      key[r] = KEY_MAX;
+      sid[r] = SID_NONE;
+    }
+  }
+  __device__ __forceinline__ u64 at_key(int p) const {
+    u64 v = 0;
+#pragma unroll
+    for (int r = 0; r < RL; ++r) {
+      u64 t = __shfl_sync(0xffffffffu, key[r], p & 31);
+      if ((p >> 5) == r) v = t;
+    }
+    return v;
+  }
+  // x / xs are warp-uniform
+  __device__ __forceinline__ void insert(u64 x, u32 xs, int lane) {
+    int pos = 0;
+#pragma unroll
+    for (int r = 0; r < RL; ++r) pos += __popc(__ballot_sync(0xffffffffu, key[r] < x));
+    if (pos >= 32 * RL) return;
+#pragma unroll
+    for (int r = RL - 1; r >= 0; --r) {
+      const int base = r * 32;
+      if (pos >= base + 32) continue;
+      u64 upk = __shfl_up_sync(0xffffffffu, key[r], 1);
+      u32 ups = __shfl_up_sync(0xffffffffu, sid[r], 1);
+      if (r > 0) {
+        u64 ck = __shfl_sync(0xffffffffu, key[r - 1], 31);
+        u32 cs = __shfl_sync(0xffffffffu, sid[r - 1], 31);
+        if (lane == 0) {
+          upk = ck;
+          ups = cs;
+        }
+      }
+      const int g = base + lane;
+      if (g == pos) {
+        key[r] = x;
+        sid[r] = xs;
+      } else if (g > pos) {
+        key[r] = upk;
+        sid[r] = ups;
+      }
+    }
+  }
+};
+
+__device__ __forceinline__ u32 lower_bound_u64(const u64* a, u32 n, u64 v) {
+  u32 lo = 0, hi = n;
+  while (lo < hi) {
+    u32 mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+template <int RL, bool EXTERNAL>
+__global__ void __launch_bounds__(256)
+knn_general_kernel(GridView g, const float4* __restrict__ spts, const float4* __restrict__ queries,
+                   const u32* __restrict__ list, const u32* __restrict__ count_ptr, u32 m_external,
+                   int k, u32* __restrict__ nbr, float* __restrict__ nd2, u64* __restrict__ kth) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u32 nw = (gridDim.x * blockDim.x) >> 5;
+  const u32 total = EXTERNAL ? m_external : *count_ptr;
+  WarpTopK<RL> top;
+  for (u32 it = gw; it < total; it += nw) {
+    u32 row;
+    float4 Q;
+    if (EXTERNAL) {
+      row = it;
+      Q = queries[it];
+    } else {
+      row = list[it];
+      Q = spts[row];
+    }
+    const double vx = ((double)Q.x - g.ox) * g.inv_cell, vy = ((double)Q.y - g.oy) * g.inv_cell,
+                 vz = ((double)Q.z - g.oz) * g.inv_cell;
+    const int cx = min(g.dimx - 1, max(0, (int)floor(vx)));
+    const int cy = min(g.dimy - 1, max(0, (int)floor(vy)));
+    const int cz = min(g.dimz - 1, max(0, (int)floor(vz)));
+    for (int j = 0;; ++j) {
+      top.reset();
+      const int sx = cx >> j, sy = cy >> j, sz = cz >> j;
+      const int sdx = ((g.dimx - 1) >> j) + 1, sdy = ((g.dimy - 1) >> j) + 1, sdz = ((g.dimz - 1) >> j) + 1;
+      // point ranges of the 27 super-cells (Morton prefix ranges)
+      u32 pstart = 0, pend = 0;
+      if (lane < 27) {
+        int x = sx + (lane % 3) - 1, y = sy + ((lane / 3) % 3) - 1, z = sz + (lane / 9) - 1;
+        if (x >= 0 && x < sdx && y >= 0 && y < sdy && z >= 0 && z < sdz) {
+          u64 pfx = morton3((u32)x, (u32)y, (u32)z);
+          u64 klo = pfx << (3 * j), khi = (pfx + 1) << (3 * j);
+          u32 a = lower_bound_u64(g.cell_key, g.n_cells, klo);
+          u32 b = lower_bound_u64(g.cell_key, g.n_cells, khi);
+          pstart = g.cell_start[a];
+          pend = g.cell_start[b];
+        }
+      }
+      for (int c27 = 0; c27 < 27; ++c27) {
+        u32 s = __shfl_sync(FULL, pstart, c27), e = __shfl_sync(FULL, pend, c27);
+        for (u32 base = s; base < e; base += 32) {
+          u32 pi = base + lane;
+          u64 ck = KEY_MAX;
+          if (pi < e) {
+            float4 P = spts[pi];
+            ck = make_key(dist2_exact(Q.x, Q.y, Q.z, P.x, P.y, P.z), __float_as_uint(P.w));
+          }
+          u64 thr = top.at_key(k - 1);
+          unsigned mask = __ballot_sync(FULL, ck < thr);
+          while (mask) {
+            int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            u64 x = __shfl_sync(FULL, ck, src);
+            top.insert(x, base + (u32)src, lane);
+          }
+        }
+      }
+      // distance from the query to the nearest unscanned cell: faces of the block
+      // that still have cells behind them
+      const double cs = g.cell * (double)(1 << j);
+      double bound = INFINITY;
+      {
+        int bx0 = max(sx - 1, 0), bx1 = min(sx + 1, sdx - 1);
+        int by0 = max(sy - 1, 0), by1 = min(sy + 1, sdy - 1);
+        int bz0 = max(sz - 1, 0), bz1 = min(sz + 1, sdz - 1);
+        if (bx0 > 0) bound = fmin(bound, fmax(0.0, ((double)Q.x - g.ox) - bx0 * cs));
+        if (bx1 < sdx - 1) bound = fmin(bound, fmax(0.0, (bx1 + 1) * cs - ((double)Q.x - g.ox)));
+        if (by0 > 0) bound = fmin(bound, fmax(0.0, ((double)Q.y - g.oy) - by0 * cs));
+        if (by1 < sdy - 1) bound = fmin(bound, fmax(0.0, (by1 + 1) * cs - ((double)Q.y - g.oy)));
+        if (bz0 > 0) bound = fmin(bound, fmax(0.0, ((double)Q.z - g.oz) - bz0 * cs));
+        if (bz1 < sdz - 1) bound = fmin(bound, fmax(0.0, (bz1 + 1) * cs - ((double)Q.z - g.oz)));
+      }
+      if (isinf(bound)) break;  // the block covers the whole grid
+      u64 kk = top.at_key(k - 1);
+      if (kk != KEY_MAX) {
+        double b = bound * (1.0 - 1e-6);
+        float kd2 = __uint_as_float((u32)(kk >> 32));
+        if (kd2 <= __double2float_rd(b * b)) break;
+      }
+    }
+    // ---- write the row ----
+#pragma unroll
+    for (int r = 0; r < RL; ++r) {
+      int p = r * 32 + lane;
+      if (p < k) {
+        nbr[(size_t)row * k + p] = top.sid[r];
+        if (nd2)
+          nd2[(size_t)row * k + p] =
+              top.sid[r] == SID_NONE ? INFINITY : __uint_as_float((u32)(top.key[r] >> 32));
+        if (p == k - 1 && kth) kth[row] = top.key[r];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+static size_t cell_kernel_smem(int E) {
+  int CS = 32 * E;
+  return (size_t)KNN_WARPS * (KNN_CAP * 16 + CS * 8 + KNN_CAP * 4 + CS * 4) + KNN_WARPS * 4 + 16;
+}
+
+int knn_run(iftwt_ctx* c, int k) {
+  if (k < 1 || k > 64) return ctx_fail(c, IFTWT_ERR_INVALID, "k must be in [1, 64], got %d", k);
+  TRY(grid_build(c, k));
+  if (c->knn_k == k) return IFTWT_OK;
+  StageTimer st(c, IFTWT_STAGE_KNN);
+  const size_t n = c->n;
+  ENSURE(c, c->nbr, n * k * 4);
+  ENSURE(c, c->nd2, n * k * 4);
+  ENSURE(c, c->kth, n * 8);
+  ENSURE(c, c->fb_list, n * 4);
+  u32* fb_count = (u32*)(c->scalars.as<int>() + 48);
+  CU_TRY(c, cudaMemsetAsync(fb_count, 0, 4, c->stream));
+  const GridView& g = c->grid;
+  float tau0 = (float)(g.cell * g.cell * 0.6);
+  const float4* spts = c->spts.as<float4>();
+  unsigned blocks = div_up(g.n_cells, KNN_WARPS);
+  if (k <= 32) {
+    size_t sm = cell_kernel_smem(2);
+    CU_TRY(c, cudaFuncSetAttribute(knn_cell_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    LAUNCH(c, knn_cell_kernel<2>, blocks, KNN_WARPS * 32, sm, g, spts, c->qb2.as<float>(), k, tau0,
+           c->nbr.as<u32>(), c->nd2.as<float>(), c->kth.as<u64>(), c->fb_list.as<u32>(), fb_count);
+  } else {
+    size_t sm = cell_kernel_smem(4);
+    CU_TRY(c, cudaFuncSetAttribute(knn_cell_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    LAUNCH(c, knn_cell_kernel<4>, blocks, KNN_WARPS * 32, sm, g, spts, c->qb2.as<float>(), k, tau0,
+           c->nbr.as<u32>(), c->nd2.as<float>(), c->kth.as<u64>(), c->fb_list.as<u32>(), fb_count);
+  }
+  CHECK_LAUNCH(c);
+  unsigned gblocks = c->sm_count * 8;
+  {
+    auto kern = (k <= 32) ? knn_general_kernel<1, false> : knn_general_kernel<2, false>;
+    LAUNCH(c, kern, gblocks, 256, 0, g, spts, (const float4*)nullptr, (const u32*)c->fb_list.as<u32>(),
+           (const u32*)fb_count, 0u, k, c->nbr.as<u32>(), c->nd2.as<float>(), c->kth.as<u64>());
+  }
+  CHECK_LAUNCH(c);
+  int* hs = (int*)c->h_scalars;
+  CU_TRY(c, cudaMemcpyAsync(hs + 48, fb_count, 4, cudaMemcpyDeviceToHost, c->stream));
+  c->knn_k = k;
+  c->graph_k = 0;
+  return IFTWT_OK;
+}
+
+// external queries (device float4 {x,y,z,_}); idx in SORTED space, SID_NONE when missing
+int knn_query_run(iftwt_ctx* c, const float4* d_q, size_t m, int k, u32* d_idx_sorted, float* d_d2) {
+  if (k < 1 || k > 64) return ctx_fail(c, IFTWT_ERR_INVALID, "k must be in [1, 64], got %d", k);
+  if (!c->grid_valid) TRY(grid_build(c, k < 8 ? 8 : k));
+  if (m == 0) return IFTWT_OK;
+  unsigned gblocks = (unsigned)((m + 7) / 8);
+  if (gblocks > (unsigned)c->sm_count * 8) gblocks = c->sm_count * 8;
+  {
+    auto kern = (k <= 32) ? knn_general_kernel<1, true> : knn_general_kernel<2, true>;
+    LAUNCH(c, kern, gblocks, 256, 0, c->grid, (const float4*)c->spts.as<float4>(), d_q,
+           (const u32*)nullptr, (const u32*)nullptr, (u32)m, k, d_idx_sorted, d_d2, (u64*)nullptr);
+  }
+  CHECK_LAUNCH(c);
+  return IFTWT_OK;
+}

@@ -1,0 +1,227 @@
+// normals.cu — K3: per-point 3x3 covariance + closed-form smallest eigenpair.
+//
+// Replaces pcl::NormalEstimationOMP::compute as called at main.cpp:104-109
+// (computePointNormal -> computeMeanAndCovarianceMatrix -> solvePlaneParameters ->
+// eigen33 -> computeRoots / computeRoots2, then flipNormalTowardsViewpoint with the
+// default viewpoint (0,0,0)).  Scalar FP32, one thread per point, no tensor cores:
+// this is k gathers and a 3x3 eigenproblem, not a dense contraction.
+//
+// Bit parity with the oracle (oracle/iftwt_oracle.cpp: point_normal): the FP32
+// operation order below is the oracle's, the build uses -fmad=false so nothing is
+// contracted, division and sqrt are IEEE (nvcc defaults -prec-div/-prec-sqrt), and
+// the three elementary functions of the eigen solver are evaluated by the fixed
+// binary64 series of DESIGN.md ("spec trig") and rounded once to binary32 — every
+// step is a correctly rounded IEEE operation on both machines.
+#include "common.cuh"
+
+#define SID_NONE 0xFFFFFFFFu
+
+namespace {
+
+__device__ __forceinline__ double spec_atan_small(double u) {
+  const int N = 22;
+  double u2 = u * u;
+  double s = 1.0 / (double)(2 * N + 1);
+#pragma unroll
+  for (int n = N - 1; n >= 0; --n) s = 1.0 / (double)(2 * n + 1) - u2 * s;
+  return u * s;
+}
+__device__ __forceinline__ double spec_atan01(double t) {
+  const double kPi = 3.141592653589793;
+  if (t > 0.41421356237309503) return kPi / 4.0 + spec_atan_small((t - 1.0) / (t + 1.0));
+  return spec_atan_small(t);
+}
+__device__ __forceinline__ double spec_atan2_ypos(double y, double x) {
+  const double kPi = 3.141592653589793;
+  double ax = fabs(x);
+  if (y == 0.0) return x < 0.0 ? kPi : 0.0;
+  double r;
+  if (ax >= y) r = spec_atan01(y / ax);
+  else r = kPi / 2.0 - spec_atan01(ax / y);
+  if (x < 0.0) r = kPi - r;
+  return r;
+}
+__device__ __forceinline__ double spec_cos(double x) {
+  double x2 = x * x, c = 1.0;
+#pragma unroll
+  for (int n = 13; n >= 1; --n) c = 1.0 - (x2 / (double)((2 * n - 1) * (2 * n))) * c;
+  return c;
+}
+__device__ __forceinline__ double spec_sin(double x) {
+  double x2 = x * x, s = 1.0;
+#pragma unroll
+  for (int n = 13; n >= 1; --n) s = 1.0 - (x2 / (double)((2 * n) * (2 * n + 1))) * s;
+  return x * s;
+}
+
+__device__ __forceinline__ void compute_roots2(float b, float c, float roots[3]) {
+  roots[0] = 0.f;
+  float bb = b * b;
+  float d = (float)((double)bb - 4.0 * (double)c);
+  if (d < 0.0f) d = 0.0f;
+  float sd = sqrtf(d);
+  roots[2] = 0.5f * (b + sd);
+  roots[1] = 0.5f * (b - sd);
+}
+
+__device__ __forceinline__ void swapf(float& a, float& b) {
+  float t = a;
+  a = b;
+  b = t;
+}
+
+__device__ void compute_roots(const float m[3][3], float roots[3]) {
+  float c0 = m[0][0] * m[1][1] * m[2][2];
+  c0 = c0 + 2.0f * m[0][1] * m[0][2] * m[1][2];
+  c0 = c0 - m[0][0] * m[1][2] * m[1][2];
+  c0 = c0 - m[1][1] * m[0][2] * m[0][2];
+  c0 = c0 - m[2][2] * m[0][1] * m[0][1];
+  float c1 = m[0][0] * m[1][1];
+  c1 = c1 - m[0][1] * m[0][1];
+  c1 = c1 + m[0][0] * m[2][2];
+  c1 = c1 - m[0][2] * m[0][2];
+  c1 = c1 + m[1][1] * m[2][2];
+  c1 = c1 - m[1][2] * m[1][2];
+  float c2 = m[0][0] + m[1][1];
+  c2 = c2 + m[2][2];
+  if (fabsf(c0) < 1.1920928955078125e-07f) {  // FLT_EPSILON
+    compute_roots2(c2, c1, roots);
+    return;
+  }
+  const float s_inv3 = (float)(1.0 / 3.0);
+  const float s_sqrt3 = 1.7320508075688772f;  // sqrtf(3.0f)
+  float c2_over_3 = c2 * s_inv3;
+  float a_over_3 = (c1 - c2 * c2_over_3) * s_inv3;
+  if (a_over_3 > 0.f) a_over_3 = 0.f;
+  float half_b = 0.5f * (c0 + c2_over_3 * (2.0f * c2_over_3 * c2_over_3 - c1));
+  float q = half_b * half_b + a_over_3 * a_over_3 * a_over_3;
+  if (q > 0.f) q = 0.f;
+  float rho = sqrtf(-a_over_3);
+  float sq = sqrtf(-q);
+  float at = (float)spec_atan2_ypos((double)sq, (double)half_b);
+  float theta = at * s_inv3;
+  float cos_theta = (float)spec_cos((double)theta);
+  float sin_theta = (float)spec_sin((double)theta);
+  roots[0] = c2_over_3 + 2.0f * rho * cos_theta;
+  roots[1] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
+  roots[2] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);
+  if (roots[0] >= roots[1]) swapf(roots[0], roots[1]);
+  if (roots[1] >= roots[2]) {
+    swapf(roots[1], roots[2]);
+    if (roots[0] >= roots[1]) swapf(roots[0], roots[1]);
+  }
+  if (roots[0] <= 0.f) compute_roots2(c2, c1, roots);
+}
+
+__device__ __forceinline__ void cross3(const float a[3], const float b[3], float o[3]) {
+  o[0] = a[1] * b[2] - a[2] * b[1];
+  o[1] = a[2] * b[0] - a[0] * b[2];
+  o[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ float sqnorm3(const float v[3]) {
+  return v[0] * v[0] + (v[1] * v[1] + v[2] * v[2]);
+}
+
+__global__ void __launch_bounds__(128)
+normals_kernel(const float4* __restrict__ spts, const u32* __restrict__ nbr, u32 n, int k,
+               float4* __restrict__ out) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u32* row = nbr + (size_t)i * k;
+  int cnt = 0;
+  float a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0;
+  for (int j = 0; j < k; ++j) {
+    u32 v = row[j];
+    if (v == SID_NONE) continue;
+    float4 p = spts[v];
+    a0 += p.x * p.x;
+    a1 += p.x * p.y;
+    a2 += p.x * p.z;
+    a3 += p.y * p.y;
+    a4 += p.y * p.z;
+    a5 += p.z * p.z;
+    a6 += p.x;
+    a7 += p.y;
+    a8 += p.z;
+    ++cnt;
+  }
+  float4 res;
+  if (cnt < 3) {
+    float nanv = __int_as_float(0x7FC00000);
+    res = make_float4(nanv, nanv, nanv, nanv);
+    out[i] = res;
+    return;
+  }
+  float fc = (float)cnt;
+  a0 /= fc; a1 /= fc; a2 /= fc; a3 /= fc; a4 /= fc; a5 /= fc; a6 /= fc; a7 /= fc; a8 /= fc;
+  float cov[3][3];
+  cov[0][0] = a0 - a6 * a6;
+  cov[0][1] = a1 - a6 * a7;
+  cov[0][2] = a2 - a6 * a8;
+  cov[1][1] = a3 - a7 * a7;
+  cov[1][2] = a4 - a7 * a8;
+  cov[2][2] = a5 - a8 * a8;
+  cov[1][0] = cov[0][1];
+  cov[2][0] = cov[0][2];
+  cov[2][1] = cov[1][2];
+  float scale = 0.f;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) scale = fmaxf(scale, fabsf(cov[r][cc]));
+  if (scale <= 1.17549435e-38f) scale = 1.0f;  // FLT_MIN
+  float sm[3][3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) sm[r][cc] = cov[r][cc] / scale;
+  float roots[3];
+  compute_roots(sm, roots);
+  float eigenvalue = roots[0] * scale;
+  sm[0][0] -= roots[0];
+  sm[1][1] -= roots[0];
+  sm[2][2] -= roots[0];
+  float v1[3], v2[3], v3[3];
+  cross3(sm[0], sm[1], v1);
+  cross3(sm[0], sm[2], v2);
+  cross3(sm[1], sm[2], v3);
+  float l1 = sqnorm3(v1), l2 = sqnorm3(v2), l3 = sqnorm3(v3);
+  float nx, ny, nz;
+  if (l1 >= l2 && l1 >= l3) {
+    float s = sqrtf(l1);
+    nx = v1[0] / s; ny = v1[1] / s; nz = v1[2] / s;
+  } else if (l2 >= l1 && l2 >= l3) {
+    float s = sqrtf(l2);
+    nx = v2[0] / s; ny = v2[1] / s; nz = v2[2] / s;
+  } else {
+    float s = sqrtf(l3);
+    nx = v3[0] / s; ny = v3[1] / s; nz = v3[2] / s;
+  }
+  float eig_sum = cov[0][0] + cov[1][1];
+  eig_sum = eig_sum + cov[2][2];
+  float curvature = (eig_sum != 0.f) ? fabsf(eigenvalue / eig_sum) : 0.f;
+  float4 self = spts[i];
+  float vx = 0.f - self.x, vy = 0.f - self.y, vz = 0.f - self.z;
+  float ct = vx * nx + vy * ny;
+  ct = ct + vz * nz;
+  if (ct < 0.f) {
+    nx *= -1.f; ny *= -1.f; nz *= -1.f;
+  }
+  out[i] = make_float4(nx, ny, nz, curvature);
+}
+
+}  // namespace
+
+int normals_run(iftwt_ctx* c) {
+  if (c->knn_k == 0) return ctx_fail(c, IFTWT_ERR_STATE, "k-NN lists are not computed");
+  if (c->nrm_k == c->knn_k) return IFTWT_OK;
+  StageTimer st(c, IFTWT_STAGE_NORMALS);
+  const u32 n = (u32)c->n;
+  ENSURE(c, c->nrm, (size_t)n * 16);
+  LAUNCH(c, normals_kernel, div_up(n, 128), 128, 0, c->spts.as<float4>(), c->nbr.as<u32>(), n, c->knn_k,
+         c->nrm.as<float4>());
+  CHECK_LAUNCH(c);
+  c->nrm_k = c->knn_k;
+  c->seeds_valid = false;
+  return IFTWT_OK;
+}

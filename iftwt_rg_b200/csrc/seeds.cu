@@ -1,0 +1,361 @@
+// seeds.cu — K4 / K4': region-growing seed selection.
+//
+// Replaces FlatPoint::getCentroidsCloud (flat_point.hpp:50-56 -> compute_centroid_info
+// 65-91 -> getCentroids 23-42 -> pcl::RegionGrowing::extract, parameters main.cpp:112-119).
+//
+// PCL's region growing is a sequential seeded BFS over points sorted by curvature.
+// With the curvature gate inactive (it is for the reference's settings: curvature
+// <= 1/3 < threshold 1.0) its result has an exact order-free form (SURVEY App. A.4,
+// proved against the literal procedure in tests/test_oracle_ift_rg.py):
+//     segment(v) = min rank over all u that reach v along arcs u -> w,
+//                  w in kNN(u), |n_u . n_w| >= cos(theta),
+// rank = position in the (curvature, index) order.  It is computed here as
+//   1. ranks by one radix sort of (curvature bits, original index);
+//   2. union-find over the MUTUAL smooth arcs (both u in kNN(w) and w in kNN(u);
+//      the test itself is symmetric), hooking + pointer jumping, O(log) depth;
+//   3. component min-rank, then label-min sweeps over the remaining ONE-WAY smooth
+//      arcs between components until nothing changes;
+//   4. segment sizes, the [min, max] filter, PCL's emission order (ascending seed
+//      rank), and the literal FP32 centroid: pcl::compute3DCentroid sums a
+//      cluster's points in ascending point index (assembleRegions order), so the
+//      members are sorted by (cluster, index) and one thread per cluster adds them
+//      sequentially;
+//   5. the snap of every centroid to its nearest input point (k-NN general path).
+#include <cub/cub.cuh>
+#include <math.h>
+
+#include "common.cuh"
+
+#define SID_NONE 0xFFFFFFFFu
+
+namespace {
+
+__device__ __forceinline__ u32 uf_find(u32* parent, u32 v) {
+  u32 p = parent[v];
+  while (p != v) {
+    u32 gp = parent[p];
+    if (gp != p) parent[v] = gp;  // path halving (benign race)
+    v = p;
+    p = gp;
+  }
+  return v;
+}
+__device__ __forceinline__ void uf_union(u32* parent, u32 a, u32 b) {
+  u32 ra = uf_find(parent, a), rb = uf_find(parent, b);
+  while (ra != rb) {
+    if (ra < rb) {
+      u32 ret = atomicCAS(&parent[rb], rb, ra);
+      if (ret == rb) return;
+      rb = ret;
+    } else {
+      u32 ret = atomicCAS(&parent[ra], ra, rb);
+      if (ret == ra) return;
+      ra = ret;
+    }
+  }
+}
+
+// Eigen's unrolled 3-element reduction: e0 + (e1 + e2)   (oracle: dot3_eigen)
+__device__ __forceinline__ bool smooth_pass(const float4 nu, const float4 nv, float cos_thr) {
+  float dp = fabsf(nv.x * nu.x + (nv.y * nu.y + nv.z * nu.z));
+  return !(dp < cos_thr);  // NaN passes, as in PCL
+}
+
+__global__ void rank_keys_kernel(const float4* __restrict__ nrm, const float4* __restrict__ spts, u32 n,
+                                 u64* __restrict__ keys, u32* __restrict__ vals, u32* __restrict__ parent) {
+  u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  keys[j] = ((u64)__float_as_uint(nrm[j].w) << 32) | (u64)__float_as_uint(spts[j].w);
+  vals[j] = j;
+  parent[j] = j;
+}
+__global__ void scatter_rank_kernel(const u32* __restrict__ sorted_vals, u32 n, u32* __restrict__ rank) {
+  u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  rank[sorted_vals[r]] = r;
+}
+
+// pass 0: union mutual smooth arcs, count one-way smooth arcs.  pass 1: also emit them.
+__global__ void rg_arcs_kernel(const u32* __restrict__ nbr, const float* __restrict__ nd2,
+                               const u64* __restrict__ kth, const float4* __restrict__ spts,
+                               const float4* __restrict__ nrm, size_t n_entries, int k, float cos_thr,
+                               u32* __restrict__ parent, int pass, u32* __restrict__ counter,
+                               u32* __restrict__ arc_u, u32* __restrict__ arc_v) {
+  size_t a = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool oneway = false;
+  u32 u = 0, v = 0;
+  if (a < n_entries) {
+    u = (u32)(a / k);
+    v = nbr[a];
+    if (v != SID_NONE && v != u && smooth_pass(nrm[u], nrm[v], cos_thr)) {
+      u64 key = ((u64)__float_as_uint(nd2[a]) << 32) | (u64)__float_as_uint(spts[u].w);
+      if (key <= kth[v]) {
+        if (pass == 0 && u > v) uf_union(parent, u, v);  // the twin arc v->u does the same union
+      } else {
+        oneway = true;
+      }
+    }
+  }
+  unsigned m = __ballot_sync(0xffffffffu, oneway);
+  if (m == 0) return;
+  int lane = threadIdx.x & 31;
+  u32 base = 0;
+  if (lane == 0) base = atomicAdd(counter, (u32)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (oneway && pass == 1) {
+    u32 p = base + __popc(m & ((1u << lane) - 1u));
+    arc_u[p] = u;
+    arc_v[p] = v;
+  }
+}
+
+__global__ void rg_flatten_kernel(u32* __restrict__ parent, const u32* __restrict__ rank, u32 n,
+                                  u32* __restrict__ L) {
+  u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  u32 r = uf_find(parent, v);
+  parent[v] = r;
+  atomicMin(&L[r], rank[v]);
+}
+// arcs to root space
+__global__ void rg_arcs_to_roots_kernel(const u32* __restrict__ parent, u32 m, u32* __restrict__ arc_u,
+                                        u32* __restrict__ arc_v) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  arc_u[i] = parent[arc_u[i]];
+  arc_v[i] = parent[arc_v[i]];
+}
+__global__ void rg_sweep_kernel(const u32* __restrict__ arc_u, const u32* __restrict__ arc_v, u32 m,
+                                u32* __restrict__ L, u32* __restrict__ changed) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  u32 ru = arc_u[i], rv = arc_v[i];
+  if (ru == rv) return;
+  u32 a = L[ru];
+  if (a < L[rv]) {
+    atomicMin(&L[rv], a);
+    *changed = 1u;
+  }
+}
+// per point: segment = L[root]; count sizes by seed rank
+__global__ void rg_sizes_kernel(const u32* __restrict__ parent, const u32* __restrict__ L, u32 n,
+                                u32* __restrict__ seg_of, u32* __restrict__ size_by_rank) {
+  u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  u32 s = L[parent[v]];
+  seg_of[v] = s;
+  atomicAdd(&size_by_rank[s], 1u);
+}
+__global__ void rg_keep_flags_kernel(const u32* __restrict__ size_by_rank, u32 n, u32 min_sz, u32 max_sz,
+                                     u32* __restrict__ keep, u32* __restrict__ nseg) {
+  u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+  u32 s = r < n ? size_by_rank[r] : 0u;
+  bool any = s > 0;
+  if (r < n) keep[r] = (s >= min_sz && s <= max_sz) ? 1u : 0u;
+  unsigned m = __ballot_sync(0xffffffffu, any);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(nseg, (u32)__popc(m));
+}
+// kept cluster table: size of kept cluster c (c = kept_id[rank])
+__global__ void rg_kept_sizes_kernel(const u32* __restrict__ size_by_rank, const u32* __restrict__ keep,
+                                     const u32* __restrict__ kept_id, u32 n, u32* __restrict__ ksize) {
+  u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n || !keep[r]) return;
+  ksize[kept_id[r]] = size_by_rank[r];
+}
+// member keys in ORIGINAL order: (kept cluster << 32 | original index) or ~0
+__global__ void rg_member_keys_kernel(const u32* __restrict__ seg_of, const u32* __restrict__ keep,
+                                      const u32* __restrict__ kept_id, const u32* __restrict__ inv, u32 n,
+                                      u64* __restrict__ keys, int* __restrict__ point_label) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u32 s = seg_of[inv[i]];
+  bool kp = keep[s] != 0;
+  u32 c = kp ? kept_id[s] : 0u;
+  keys[i] = kp ? (((u64)c << 32) | (u64)i) : 0xFFFFFFFFFFFFFFFFull;
+  point_label[i] = kp ? (int)c : -1;
+}
+// one thread per kept cluster: pcl::compute3DCentroid, FP32, ascending point index
+__global__ void rg_centroid_kernel(const u64* __restrict__ sorted_keys, const u32* __restrict__ kstart,
+                                   const u32* __restrict__ ksize, u32 n_kept,
+                                   const float4* __restrict__ pts_in, float4* __restrict__ centroid) {
+  u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_kept) return;
+  u32 b = kstart[c], cnt = ksize[c];
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll 8
+  for (u32 t = 0; t < cnt; ++t) {
+    u32 i = (u32)sorted_keys[b + t];
+    float4 p = pts_in[i];
+    sx += p.x;
+    sy += p.y;
+    sz += p.z;
+  }
+  float d = (float)cnt;
+  centroid[c] = make_float4(sx / d, sy / d, sz / d, 0.f);
+}
+__global__ void rg_seed_ids_kernel(const u32* __restrict__ sid_sorted, const u32* __restrict__ perm, u32 m,
+                                   u32* __restrict__ seeds) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  u32 s = sid_sorted[i];
+  seeds[i] = s == SID_NONE ? SID_NONE : perm[s];
+}
+
+}  // namespace
+
+int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p) {
+  if (c->nrm_k == 0) return ctx_fail(c, IFTWT_ERR_STATE, "normals are not computed (call iftwt_normals first)");
+  if (p->number_of_neighbours != c->knn_k) {
+    // region growing wants its own neighbourhood size: recompute the lists on the same grid
+    TRY(knn_run(c, p->number_of_neighbours));
+  }
+  StageTimer st(c, IFTWT_STAGE_SEEDS);
+  const u32 n = (u32)c->n;
+  const int k = c->knn_k;
+  const size_t ne = (size_t)n * k;
+  const float4* nrm = c->nrm.as<float4>();
+  const float4* spts = c->spts.as<float4>();
+  u32* sc = (u32*)c->scalars.as<int>();
+  u32* hs = (u32*)c->h_scalars;
+
+  // the exact parallel form needs the curvature gate to be inactive
+  // (curvature = |lambda0 / trace| <= 1/3 for a PSD covariance; NaN never compares greater)
+  if (!(p->curvature_threshold >= 0.34f))
+    return ctx_fail(c, IFTWT_ERR_UNSUPPORTED,
+                    "curvature_threshold %.3f can fire; the GPU restatement of RegionGrowing is exact only "
+                    "when it cannot (threshold >= 0.34, reference uses 1.0)", p->curvature_threshold);
+  const float cos_thr = cosf(p->smoothness_threshold);
+
+  // 1. ranks
+  ENSURE(c, c->keys, (size_t)n * 8);
+  ENSURE(c, c->keys_alt, (size_t)n * 8);
+  ENSURE(c, c->vals_alt, (size_t)n * 4);
+  ENSURE(c, c->rg_rank, (size_t)n * 4);
+  ENSURE(c, c->rg_parent, (size_t)n * 4);
+  ENSURE(c, c->rg_label, (size_t)n * 4);
+  ENSURE(c, c->rg_aux, (size_t)n * 4 * 4);
+  u32* rank = c->rg_rank.as<u32>();
+  u32* parent = c->rg_parent.as<u32>();
+  u32* L = c->rg_label.as<u32>();
+  u32* seg_of = c->rg_aux.as<u32>();
+  u32* size_by_rank = seg_of + n;
+  u32* keep = size_by_rank + n;
+  u32* kept_id = keep + n;
+  {
+    u64* k0 = c->keys.as<u64>();
+    u64* k1 = c->keys_alt.as<u64>();
+    u32* v0 = c->vals_alt.as<u32>();
+    u32* v1 = seg_of;  // scratch
+    LAUNCH(c, rank_keys_kernel, div_up(n, 256), 256, 0, nrm, spts, n, k0, v0, parent);
+    size_t tb = 0;
+    CU_TRY(c, cub::DeviceRadixSort::SortPairs(nullptr, tb, k0, k1, v0, v1, (int)n, 0, 64, c->stream));
+    ENSURE(c, c->tmp, tb);
+    CU_TRY(c, cub::DeviceRadixSort::SortPairs(c->tmp.p, tb, k0, k1, v0, v1, (int)n, 0, 64, c->stream));
+    c->stats.kernel_launches += 10;
+    LAUNCH(c, scatter_rank_kernel, div_up(n, 256), 256, 0, v1, n, rank);
+    CHECK_LAUNCH(c);
+  }
+  // 2. mutual smooth arcs -> union-find; count one-way smooth arcs
+  u32* d_cnt = sc + 56;
+  CU_TRY(c, cudaMemsetAsync(d_cnt, 0, 16, c->stream));
+  LAUNCH(c, rg_arcs_kernel, div_up(ne, 256), 256, 0, c->nbr.as<u32>(), c->nd2.as<float>(), c->kth.as<u64>(),
+         spts, nrm, ne, k, cos_thr, parent, 0, d_cnt, (u32*)nullptr, (u32*)nullptr);
+  CHECK_LAUNCH(c);
+  CU_TRY(c, cudaMemcpyAsync(hs + 56, d_cnt, 4, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  const u32 n_oneway = hs[56];
+  ENSURE(c, c->rg_aux2, ((size_t)n_oneway + 1) * 8);
+  u32* arc_u = c->rg_aux2.as<u32>();
+  u32* arc_v = arc_u + (n_oneway + 1);
+  if (n_oneway) {
+    LAUNCH(c, rg_arcs_kernel, div_up(ne, 256), 256, 0, c->nbr.as<u32>(), c->nd2.as<float>(),
+           c->kth.as<u64>(), spts, nrm, ne, k, cos_thr, parent, 1, d_cnt + 1, arc_u, arc_v);
+    CHECK_LAUNCH(c);
+  }
+  // 3. component min rank, then label-min over one-way arcs
+  CU_TRY(c, cudaMemsetAsync(L, 0xFF, (size_t)n * 4, c->stream));
+  LAUNCH(c, rg_flatten_kernel, div_up(n, 256), 256, 0, parent, rank, n, L);
+  CHECK_LAUNCH(c);
+  u64 sweeps = 0;
+  if (n_oneway) {
+    LAUNCH(c, rg_arcs_to_roots_kernel, div_up(n_oneway, 256), 256, 0, parent, n_oneway, arc_u, arc_v);
+    u32* d_changed = sc + 60;
+    while (true) {
+      CU_TRY(c, cudaMemsetAsync(d_changed, 0, 4, c->stream));
+      for (int b = 0; b < 4; ++b) {
+        LAUNCH(c, rg_sweep_kernel, div_up(n_oneway, 256), 256, 0, arc_u, arc_v, n_oneway, L, d_changed);
+        ++sweeps;
+      }
+      CHECK_LAUNCH(c);
+      CU_TRY(c, cudaMemcpyAsync(hs + 60, d_changed, 4, cudaMemcpyDeviceToHost, c->stream));
+      CU_TRY(c, cudaStreamSynchronize(c->stream));
+      if (hs[60] == 0) break;
+      if (sweeps > 400000) return ctx_fail(c, IFTWT_ERR_CUDA, "region growing did not converge");
+    }
+  }
+  c->stats.rg_sweeps = sweeps;
+  // 4. sizes, filter, emission order
+  CU_TRY(c, cudaMemsetAsync(size_by_rank, 0, (size_t)n * 4, c->stream));
+  CU_TRY(c, cudaMemsetAsync(sc + 61, 0, 4, c->stream));
+  LAUNCH(c, rg_sizes_kernel, div_up(n, 256), 256, 0, parent, L, n, seg_of, size_by_rank);
+  LAUNCH(c, rg_keep_flags_kernel, div_up(n, 256), 256, 0, size_by_rank, n, (u32)max(p->min_cluster_size, 0),
+         (u32)max(p->max_cluster_size, 0), keep, sc + 61);
+  CHECK_LAUNCH(c);
+  {
+    size_t tb = 0;
+    CU_TRY(c, cub::DeviceScan::ExclusiveSum(nullptr, tb, keep, kept_id, (int)n, c->stream));
+    ENSURE(c, c->tmp, tb);
+    CU_TRY(c, cub::DeviceScan::ExclusiveSum(c->tmp.p, tb, keep, kept_id, (int)n, c->stream));
+    c->stats.kernel_launches += 2;
+  }
+  // n_kept = kept_id[n-1] + keep[n-1]
+  CU_TRY(c, cudaMemcpyAsync(hs + 62, kept_id + (n - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(hs + 63, keep + (n - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(hs + 61, sc + 61, 4, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  const u32 n_kept = hs[62] + hs[63];
+  c->stats.rg_segments = hs[61];
+  // point labels (original order) + member keys
+  ENSURE(c, c->out_a, (size_t)n * 4);
+  int* point_label = c->out_a.as<int>();
+  u64* mkeys = c->keys.as<u64>();
+  u64* mkeys_sorted = c->keys_alt.as<u64>();
+  LAUNCH(c, rg_member_keys_kernel, div_up(n, 256), 256, 0, seg_of, keep, kept_id, c->inv.as<u32>(), n, mkeys,
+         point_label);
+  CHECK_LAUNCH(c);
+  c->n_seeds = n_kept;
+  ENSURE(c, c->seeds, ((size_t)n_kept + 1) * 4);
+  if (n_kept) {
+    int kbits = 1;
+    while ((1u << kbits) < n_kept + 1) ++kbits;  // +1: the all-ones key of dropped points sorts last
+    size_t tb = 0;
+    CU_TRY(c, cub::DeviceRadixSort::SortKeys(nullptr, tb, mkeys, mkeys_sorted, (int)n, 0, 64, c->stream));
+    ENSURE(c, c->tmp, tb);
+    CU_TRY(c, cub::DeviceRadixSort::SortKeys(c->tmp.p, tb, mkeys, mkeys_sorted, (int)n, 0, 64, c->stream));
+    c->stats.kernel_launches += 10;
+    (void)kbits;
+    // kept cluster sizes / starts
+    ENSURE(c, c->out_b, ((size_t)n_kept + 1) * 4 * 3 + (size_t)n_kept * 16 + 64);
+    u32* ksize = c->out_b.as<u32>();
+    u32* kstart = ksize + (n_kept + 1);
+    u32* sid = kstart + (n_kept + 1);
+    float4* centroid = (float4*)(((uintptr_t)(sid + (n_kept + 1)) + 15) & ~(uintptr_t)15);
+    LAUNCH(c, rg_kept_sizes_kernel, div_up(n, 256), 256, 0, size_by_rank, keep, kept_id, n, ksize);
+    size_t tb2 = 0;
+    CU_TRY(c, cub::DeviceScan::ExclusiveSum(nullptr, tb2, ksize, kstart, (int)n_kept, c->stream));
+    ENSURE(c, c->tmp, tb2);
+    CU_TRY(c, cub::DeviceScan::ExclusiveSum(c->tmp.p, tb2, ksize, kstart, (int)n_kept, c->stream));
+    c->stats.kernel_launches += 2;
+    LAUNCH(c, rg_centroid_kernel, div_up(n_kept, 64), 64, 0, mkeys_sorted, kstart, ksize, n_kept,
+           c->pts_in.as<float4>(), centroid);
+    CHECK_LAUNCH(c);
+    // 5. snap to the nearest input point
+    TRY(knn_query_run(c, centroid, n_kept, 1, sid, nullptr));
+    LAUNCH(c, rg_seed_ids_kernel, div_up(n_kept, 256), 256, 0, sid, c->perm.as<u32>(), n_kept,
+           c->seeds.as<u32>());
+    CHECK_LAUNCH(c);
+  }
+  c->seeds_valid = true;
+  c->stats.n_seeds = n_kept;
+  return IFTWT_OK;
+}

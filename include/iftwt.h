@@ -1,0 +1,186 @@
+/* iftwt.h — C ABI of the B200-native IFT-WT segmentation hot path.
+ *
+ * Drop-in boundary for enemy537/IFTWT_RG.  The reference has no plugin / FFI
+ * interface of its own: its boundary is the set of C++ constructors and getters
+ * that the pipeline block main.cpp:91-129 calls.  Each entry point below names
+ * the reference interface it replaces (file:line in /root/reference); the
+ * header-only adapters in include/iftwt_adapters.hpp keep the reference's class
+ * and method names on top of this ABI.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, returns int (0 = IFTWT_OK, < 0 =
+ *     error), never throws.  iftwt_last_error(ctx) gives the message.
+ *   - every index in and out of this ABI is an ORIGINAL point index (the order
+ *     of the cloud passed to iftwt_set_cloud); the Morton order used on the
+ *     device never leaks.
+ *   - the caller owns every host buffer.  An output pointer may be NULL: the
+ *     stage still runs and its result stays device resident for the next stage.
+ *   - a ctx owns one CUDA device, one stream and all device memory; it is not
+ *     re-entrant.  Different ctxs are independent (batch data-parallelism uses
+ *     one ctx per GPU / per process).
+ *   - there is no CPU fallback: every entry point fails with IFTWT_ERR_CUDA if
+ *     no sm_100 device is usable.
+ */
+#ifndef IFTWT_H
+#define IFTWT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IFTWT_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define IFTWT_API __attribute__((visibility("default")))
+#else
+#define IFTWT_API
+#endif
+
+enum {
+  IFTWT_OK = 0,
+  IFTWT_ERR_INVALID = -1,     /* bad argument */
+  IFTWT_ERR_CUDA = -2,        /* CUDA runtime failure / no device */
+  IFTWT_ERR_STATE = -3,       /* stage called before its inputs exist */
+  IFTWT_ERR_NONFINITE = -4,   /* cloud holds NaN / Inf coordinates */
+  IFTWT_ERR_UNSUPPORTED = -5, /* parameter combination the GPU path cannot restate exactly */
+  IFTWT_ERR_CAPACITY = -6,    /* caller buffer too small (needed size is reported) */
+  IFTWT_ERR_WEIGHTS = -7      /* IFT weights are negative or not integer valued (App. B #6) */
+};
+
+/* ift.hpp:1-2 */
+#define IFTWT_MAX_COST 500u
+#define IFTWT_MIN_COST 0u
+
+typedef struct iftwt_ctx iftwt_ctx;
+
+/* pcl::RegionGrowing setters used at main.cpp:111-119. */
+typedef struct iftwt_rg_params {
+  int min_cluster_size;       /* setMinClusterSize       (main.cpp:112, 50)      */
+  int max_cluster_size;       /* setMaxClusterSize       (main.cpp:113, 10000)   */
+  int number_of_neighbours;   /* setNumberOfNeighbours   (main.cpp:115, 50)      */
+  float smoothness_threshold; /* setSmoothnessThreshold  (main.cpp:118, 3 deg in rad) */
+  float curvature_threshold;  /* setCurvatureThreshold   (main.cpp:119, 1.0)     */
+} iftwt_rg_params;
+
+/* Whole pipeline of main.cpp:97-123 in one call (k-NN graph builder (B)). */
+typedef struct iftwt_segment_params {
+  int k_graph;   /* neighbours of the symmetric k-NN graph the IFT runs on            */
+  int k_normals; /* setKSearch of the normal estimation (main.cpp:108, 30)            */
+  iftwt_rg_params rg;
+  int weights;   /* 0: vertex intensity (what ift.hpp:198 reads), 1: morphological
+                    gradient dilate-erode of the intensity on the graph (graph.hpp:147-163) */
+} iftwt_segment_params;
+
+/* Stage ids for iftwt_stage_ms(). */
+enum {
+  IFTWT_STAGE_UPLOAD = 0,  /* host -> device copy of the cloud                */
+  IFTWT_STAGE_GRID = 1,    /* bbox, cell-size estimate, Morton sort, cell hash */
+  IFTWT_STAGE_KNN = 2,     /* k-NN kernels                                     */
+  IFTWT_STAGE_GRAPH = 3,   /* symmetric CSR build                              */
+  IFTWT_STAGE_NORMALS = 4, /* covariance + eigen kernel                        */
+  IFTWT_STAGE_SEEDS = 5,   /* region growing, centroids, snap                  */
+  IFTWT_STAGE_IFT = 6,     /* watershed                                        */
+  IFTWT_STAGE_DOWNLOAD = 7,
+  IFTWT_STAGE_COUNT = 8
+};
+
+typedef struct iftwt_stats {
+  uint64_t n_points;
+  uint64_t n_cells;          /* occupied grid cells                                   */
+  double cell_size;
+  uint64_t knn_fallback;     /* queries that left the one-ring fast path              */
+  uint64_t n_arcs;           /* directed arcs of the last graph                       */
+  uint64_t rg_segments;      /* region-growing segments before the size filter        */
+  uint64_t rg_sweeps;        /* label-min sweeps over one-way arcs                    */
+  uint64_t n_seeds;          /* distinct IFT seeds                                    */
+  uint64_t ift_levels;       /* non-empty cost levels processed                       */
+  uint64_t kernel_launches;  /* kernels launched by this ctx since iftwt_reset_counters */
+  uint64_t device_bytes;     /* device memory currently held                          */
+} iftwt_stats;
+
+IFTWT_API int iftwt_version(void);
+
+/* Lifetime.  `device` is a CUDA ordinal.  Replaces nothing in the reference
+ * (it has no context object; everything is process-global). */
+IFTWT_API int iftwt_create(iftwt_ctx** out, int device);
+IFTWT_API void iftwt_destroy(iftwt_ctx* ctx);
+IFTWT_API const char* iftwt_last_error(const iftwt_ctx* ctx); /* valid until the next call on ctx; ctx may be NULL */
+
+/* Input cloud.  Replaces Graph::Graph(CloudI::Ptr) / setInputCloud
+ * (graph.hpp:34-57) and NormalEstimationOMP::setInputCloud (main.cpp:107).
+ * `points` is an array of `n` records `stride_bytes` apart; xyz are three
+ * consecutive floats at byte offset `xyz_offset`, intensity one float at
+ * `intensity_offset` (or -1: intensity 0).  This accepts pcl::PointXYZI (stride
+ * 32, offsets 0 / 16), pcl::PointXYZ (16, 0, -1) and packed float4 (16, 0, 12)
+ * without repacking on the host. */
+IFTWT_API int iftwt_set_cloud(iftwt_ctx* ctx, const void* points, size_t stride_bytes, size_t n,
+                    int xyz_offset, int intensity_offset);
+/* Same, from a device-resident packed float4 {x,y,z,intensity} array on ctx's device. */
+IFTWT_API int iftwt_set_cloud_device(iftwt_ctx* ctx, const void* device_float4, size_t n);
+
+/* Exact k-NN of every cloud point (self included, first).  Replaces
+ * pcl::search::KdTree::nearestKSearch(index, k, ...) as called at graph.hpp:245
+ * and inside PCL at main.cpp:108 / 115.  Rows are in canonical (d2, index)
+ * order; missing neighbours (n < k) are -1 / +inf.  idx: n*k, d2: n*k or NULL. */
+IFTWT_API int iftwt_knn(iftwt_ctx* ctx, int k, int32_t* idx, float* d2);
+
+/* Exact k-NN of arbitrary query points against the cloud.  Replaces
+ * Graph::find_p (graph.hpp:260-266), flat_point.hpp:74 and ift.hpp:135.
+ * queries: m records of 3 floats, `stride_bytes` apart. */
+IFTWT_API int iftwt_knn_query(iftwt_ctx* ctx, const void* queries, size_t stride_bytes, size_t m, int k,
+                    int32_t* idx, float* d2);
+
+/* Symmetric k-NN graph as CSR (rows ascending, no self loops, no duplicates):
+ * graph builder (B).  Replaces Graph::getAdjacencyList (graph.hpp:63-66) for the
+ * BASELINE k-NN configurations.  off: n+1 entries.  adj: `adj_capacity` entries
+ * or NULL.  *n_arcs receives the arc count (also on IFTWT_ERR_CAPACITY). */
+IFTWT_API int iftwt_knn_graph(iftwt_ctx* ctx, int k, uint32_t* off, uint32_t* adj, size_t adj_capacity,
+                    size_t* n_arcs);
+
+/* Normals + curvature.  Replaces NormalEstimationOMP::{setKSearch, compute}
+ * (main.cpp:104-109).  Writes, per point, normal xyz at byte offset
+ * `normal_offset` and curvature at `curvature_offset` of records `stride_bytes`
+ * apart (pcl::Normal: 32, 0, 16; packed float4: 16, 0, 12).  out may be NULL. */
+IFTWT_API int iftwt_normals(iftwt_ctx* ctx, int k, void* out, size_t stride_bytes, int normal_offset,
+                  int curvature_offset);
+
+/* Region-growing seeds.  Replaces FlatPoint::getCentroidsCloud
+ * (flat_point.hpp:50-56 -> 65-91 -> 23-42 -> pcl::RegionGrowing::extract).
+ * Needs iftwt_normals first.  point_label[n] (or NULL) = index of the kept
+ * cluster, PCL emission order, or -1.  seed_index[seed_capacity] (or NULL) = the
+ * input point nearest to each kept cluster's centroid. *n_seeds = kept clusters. */
+IFTWT_API int iftwt_region_seeds(iftwt_ctx* ctx, const iftwt_rg_params* params, int32_t* point_label,
+                       int32_t* seed_index, size_t seed_capacity, size_t* n_seeds);
+
+/* IFT watershed with the f_max path cost on the current graph.  Replaces
+ * IFT_PCD::IFT_PCD(Graph&, Cloud::Ptr) (ift.hpp:31-37: copy_graph, add_seeds,
+ * compute_watershed) and getRoots (ift.hpp:48-50).
+ *   weights: n integer-valued floats in original order, or NULL = intensities.
+ *   seeds:   n_seeds vertex indices, or NULL = the seeds left on the device by
+ *            iftwt_region_seeds.
+ *   cost[n]  (or NULL): final path cost, IFTWT_MAX_COST where unreachable.
+ *   label[n] (or NULL): seed vertex that conquered the vertex (root_m,
+ *            ift.hpp:204); unreachable vertices keep label = self.
+ * Ties are broken by the "min seed" policy (policy C). */
+IFTWT_API int iftwt_ift(iftwt_ctx* ctx, const float* weights, const int32_t* seeds, size_t n_seeds,
+              uint32_t* cost, uint32_t* label);
+
+/* main.cpp:97-123 in one call: k-NN graph, normals, region-growing seeds, IFT.
+ * Everything stays on the device between stages. */
+IFTWT_API int iftwt_segment(iftwt_ctx* ctx, const iftwt_segment_params* params, uint32_t* cost,
+                  uint32_t* label, size_t* n_seeds);
+
+/* Instrumentation (the reference's is one std::time pair, ift.hpp:172-173). */
+IFTWT_API int iftwt_stage_ms(iftwt_ctx* ctx, int stage, float* ms); /* CUDA-event time of the last run of a stage */
+IFTWT_API int iftwt_get_stats(iftwt_ctx* ctx, iftwt_stats* out);
+IFTWT_API int iftwt_reset_counters(iftwt_ctx* ctx);
+IFTWT_API int iftwt_synchronize(iftwt_ctx* ctx);
+IFTWT_API void* iftwt_stream(iftwt_ctx* ctx); /* the ctx's cudaStream_t, for callers that record their own events */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IFTWT_H */
