@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py — IFT-WT segmentation throughput (BASELINE.json metric) on N B200s.
+
+A step = one pass of the hot path (k-NN graph, normals/curvature, region-growing
+seeds, IFT watershed) over one synthetic cloud per rank.
+
+  value     points/s, all ranks, cloud already resident in HBM when the timed
+            region starts, results left on the device (CUDA events, max over ranks)
+  e2e       the same through the C ABI with HOST buffers: pinned host cloud in,
+            host cost/label out, every step, inside the timed region
+  roofline  the dominant kernel (k-NN fast path) against the measured HBM peak
+  cpu_baseline  the CPU oracle (a port of the reference's CPU path; the reference
+            itself cannot be built here) on a bounded sample of the same cloud
+
+`--impl reference` times that CPU path as the reference arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from iftwt_rg_b200 import synth  # noqa: E402
+
+METRIC = "ift_wt_points_per_sec"
+UNIT = "points/s"
+WORKLOADS = {
+    # name: (generator, default n, k, description)
+    "cfg3": ("facade", 10_000_000, 32, "cfg3: synthetic 10M-point architectural facade, k=32, single B200"),
+    "cfg2": ("primitives", 1_000_000, 16, "cfg2: synthetic 1M-point plane+cylinder+sphere, k=16, single B200"),
+}
+THETA = 0.08  # smoothness threshold (rad) used for the synthetic scenes; see DESIGN.md
+RG_MIN, RG_MAX = 50, 10000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--points", type=int, default=0)
+    ap.add_argument("--k", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=400_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def make_cloud(gen: str, n: int, seed_off: int = 0) -> np.ndarray:
+    if gen == "facade":
+        return synth.scene_facade(n, seed=0x1F03 + seed_off)
+    return synth.scene_primitives(n, seed=0x1F02 + seed_off)
+
+
+def cpu_sample(gen: str, n_full: int, n_sample: int) -> np.ndarray:
+    """A spatial slab of the full cloud holding ~n_sample points: same density, same scene."""
+    if n_sample >= n_full:
+        return make_cloud(gen, n_full)
+    # generate a prefix large enough, cut an x-slab out of it scaled to the full density
+    frac = n_sample / n_full
+    pts = make_cloud(gen, n_full if n_full <= 4_000_000 else 0) if n_full <= 4_000_000 else None
+    if pts is None:
+        # stream the full cloud in chunks, keep the slab
+        keep = []
+        lo, hi = (0.0, 40.0 * frac) if gen == "facade" else (-5.0, -5.0 + 10.0 * frac * 1.6)
+        chunk = 2_000_000
+        fn = synth.scene_facade if gen == "facade" else synth.scene_primitives
+        seed = 0x1F03 if gen == "facade" else 0x1F02
+        for s in range(0, n_full, chunk):
+            c = fn(min(chunk, n_full - s), seed=seed, start=s)
+            keep.append(c[(c[:, 0] >= lo) & (c[:, 0] < hi)])
+        return np.ascontiguousarray(np.concatenate(keep))
+    xs = np.sort(pts[:, 0])
+    hi = xs[min(len(xs) - 1, n_sample)]
+    return np.ascontiguousarray(pts[pts[:, 0] < hi])
+
+
+def run_cpu_path(pts: np.ndarray, k: int) -> float:
+    """The reference's CPU path as restated by the oracle; returns seconds."""
+    from oracle import pyoracle as orc
+    t0 = time.perf_counter()
+    idx, _ = orc.knn_self(pts, k)
+    off, adj = orc.knn_graph(idx)
+    nrm = orc.normals(pts, idx)
+    lab, _, kept, _ = orc.region_growing(nrm, idx, THETA, 1.0, RG_MIN, RG_MAX)
+    seeds, _ = orc.rg_seeds(pts, lab, kept)
+    orc.ift(off, adj, pts[:, 3], seeds, orc.POLICY_R)   # faithful-fast first-offer Dial == ift.hpp:170-250
+    return time.perf_counter() - t0
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                               parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            hi = sorted(sm)[len(sm) // 2:]          # upper half = under load
+            out["sm_mhz"] = float(np.median(hi))
+            out["sm_max_mhz"] = float(max(mx))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def reference_arm(args, gen, n_full, k, desc):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pyoracle as orc
+    pts = cpu_sample(gen, n_full, args.cpu_sample)
+    for _ in range(min(args.warmup, 1)):
+        run_cpu_path(pts[: max(1000, len(pts) // 20)], k)
+    times = [run_cpu_path(pts, k) for _ in range(max(1, args.steps))]
+    t = float(np.mean(times))
+    v = len(pts) / t
+    sample = f"x-slab of the {n_full}-point cloud holding {len(pts)} points, full pipeline per step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
+        "config": {"workload": desc, "k": k, "points": n_full, "sample_points": len(pts),
+                   "note": "reference CPU path restated by oracle/ (the reference needs PCL/Boost and cannot "
+                           "be built in this image); OpenMP k-NN + normals, sequential region growing and IFT "
+                           "as in the reference"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": orc.num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    gen, n_default, k_default, desc = WORKLOADS[args.workload]
+    n = args.points or n_default
+    k = args.k or k_default
+    if args.impl == "reference":
+        reference_arm(args, gen, n, k, desc)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from iftwt_rg_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # one cloud per rank (batch data-parallel, cfg5 style): no data-path collective
+    pts = make_cloud(gen, n, seed_off=rank)
+    host_in = torch.from_numpy(pts).pin_memory()
+    dev_in = host_in.cuda(non_blocking=False)
+    host_cost = torch.empty(n, dtype=torch.int32).pin_memory()
+    host_label = torch.empty(n, dtype=torch.int32).pin_memory()
+    cost_np = host_cost.numpy().view(np.uint32)
+    label_np = host_label.numpy().view(np.uint32)
+    in_np = host_in.numpy()
+
+    ctx = api.Context(local)
+    rg = api.RgParams(RG_MIN, RG_MAX, k, THETA, 1.0)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+
+    def step_resident():
+        ctx.set_cloud_device(dev_in.data_ptr(), n)
+        ctx.segment(k, k, rg, download=False)
+
+    def step_e2e():
+        ctx.set_cloud(in_np)
+        ctx.segment(k, k, rg, cost=cost_np, label=label_np)
+
+    def timed(fn, steps):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ctx.reset_counters()
+    # per-stage device times, accumulated over the timed steps (events recorded inside the library)
+    stage_acc: dict[str, float] = {}
+
+    def step_resident_acc():
+        step_resident()
+        for s, v in ctx.stage_ms().items():
+            stage_acc[s] = stage_acc.get(s, 0.0) + v
+
+    ms_total = timed(step_resident_acc, args.steps)
+    stats = ctx.stats()
+    clocks = sampler.stop() if rank == 0 else {}
+    launches = int(stats["kernel_launches"])
+    value = world * n * args.steps / (ms_total * 1e-3)
+
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(2):
+            step_e2e()
+        ms_e2e = timed(step_e2e, args.steps)
+        e2e = {"value": world * n * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(n * 16),
+               "d2h_bytes_per_step": int(n * 8), "ms_per_step": ms_e2e / args.steps}
+
+    if rank == 0:
+        peaks = {}
+        which = "fallback"
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            which = "measured"
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        stage_ms = {s: v / args.steps for s, v in stage_acc.items()}
+        # dominant kernel: the k-NN fast path; algorithmic bytes (16 + 4k) * N per launch
+        knn_ms = stage_ms.get("knn_cell", 0.0) or stage_ms.get("knn", 0.0)
+        alg_bytes = (16 + 4 * k) * n
+        achieved = alg_bytes / (knn_ms * 1e-3) / 1e9 if knn_ms > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": "knn_cell_kernel", "achieved": achieved, "peak": peak,
+                    "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None,
+                    "peak_source": which, "algorithmic_bytes_per_launch": alg_bytes,
+                    "avg_launch_ms": knn_ms}
+        nrm_ms = stage_ms.get("normals", 0.0)
+        extra = {
+            "stage_ms": stage_ms,
+            "normals_gbs": ((32 + 4 * k) * n) / (nrm_ms * 1e-3) / 1e9 if nrm_ms > 0 else None,
+            "stats": {kk: stats[kk] for kk in ("n_cells", "cell_size", "knn_fallback", "n_arcs", "rg_segments",
+                                                "rg_sweeps", "n_seeds", "ift_levels")},
+        }
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            from oracle import pyoracle as orc
+            sample = cpu_sample(gen, n, args.cpu_sample)
+            t = run_cpu_path(sample, k)
+            cpu = {"value": len(sample) / t, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+                   "sample": f"x-slab of the cloud holding {len(sample)} points, full pipeline once ({t:.1f} s)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
+            "config": {"workload": desc if (n == n_default and k == k_default) else f"{gen} n={n} k={k}",
+                       "k": k, "points_per_gpu": n, "parallelism": f"one cloud per GPU x{world}, no collective",
+                       "l2": "inputs (16 B/pt) and every intermediate exceed the 126 MB L2; cloud re-uploaded "
+                             "device-to-device each step"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+            "cpu_baseline": cpu, "detail": extra,
+        }
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -109,21 +109,23 @@ __global__ void rg_arcs_kernel(const u32* __restrict__ nbr, const float* __restr
   }
 }
 
+// root[] is a separate array: writing the root back into parent[] would race with
+// the path halving of concurrent finds, which may overwrite it with a non-root ancestor
 __global__ void rg_flatten_kernel(u32* __restrict__ parent, const u32* __restrict__ rank, u32 n,
-                                  u32* __restrict__ L) {
+                                  u32* __restrict__ root, u32* __restrict__ L) {
   u32 v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n) return;
   u32 r = uf_find(parent, v);
-  parent[v] = r;
+  root[v] = r;
   atomicMin(&L[r], rank[v]);
 }
 // arcs to root space
-__global__ void rg_arcs_to_roots_kernel(const u32* __restrict__ parent, u32 m, u32* __restrict__ arc_u,
+__global__ void rg_arcs_to_roots_kernel(const u32* __restrict__ root, u32 m, u32* __restrict__ arc_u,
                                         u32* __restrict__ arc_v) {
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
-  arc_u[i] = parent[arc_u[i]];
-  arc_v[i] = parent[arc_v[i]];
+  arc_u[i] = root[arc_u[i]];
+  arc_v[i] = root[arc_v[i]];
 }
 __global__ void rg_sweep_kernel(const u32* __restrict__ arc_u, const u32* __restrict__ arc_v, u32 m,
                                 u32* __restrict__ L, u32* __restrict__ changed) {
@@ -138,11 +140,11 @@ __global__ void rg_sweep_kernel(const u32* __restrict__ arc_u, const u32* __rest
   }
 }
 // per point: segment = L[root]; count sizes by seed rank
-__global__ void rg_sizes_kernel(const u32* __restrict__ parent, const u32* __restrict__ L, u32 n,
+__global__ void rg_sizes_kernel(const u32* __restrict__ root, const u32* __restrict__ L, u32 n,
                                 u32* __restrict__ seg_of, u32* __restrict__ size_by_rank) {
   u32 v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n) return;
-  u32 s = L[parent[v]];
+  u32 s = L[root[v]];
   seg_of[v] = s;
   atomicAdd(&size_by_rank[s], 1u);
 }
@@ -274,11 +276,12 @@ int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p) {
   }
   // 3. component min rank, then label-min over one-way arcs
   CU_TRY(c, cudaMemsetAsync(L, 0xFF, (size_t)n * 4, c->stream));
-  LAUNCH(c, rg_flatten_kernel, div_up(n, 256), 256, 0, parent, rank, n, L);
+  u32* root = c->vals_alt.as<u32>();  // free again once the ranks are scattered
+  LAUNCH(c, rg_flatten_kernel, div_up(n, 256), 256, 0, parent, rank, n, root, L);
   CHECK_LAUNCH(c);
   u64 sweeps = 0;
   if (n_oneway) {
-    LAUNCH(c, rg_arcs_to_roots_kernel, div_up(n_oneway, 256), 256, 0, parent, n_oneway, arc_u, arc_v);
+    LAUNCH(c, rg_arcs_to_roots_kernel, div_up(n_oneway, 256), 256, 0, root, n_oneway, arc_u, arc_v);
     u32* d_changed = sc + 60;
     while (true) {
       CU_TRY(c, cudaMemsetAsync(d_changed, 0, 4, c->stream));
@@ -297,7 +300,7 @@ int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p) {
   // 4. sizes, filter, emission order
   CU_TRY(c, cudaMemsetAsync(size_by_rank, 0, (size_t)n * 4, c->stream));
   CU_TRY(c, cudaMemsetAsync(sc + 61, 0, 4, c->stream));
-  LAUNCH(c, rg_sizes_kernel, div_up(n, 256), 256, 0, parent, L, n, seg_of, size_by_rank);
+  LAUNCH(c, rg_sizes_kernel, div_up(n, 256), 256, 0, root, L, n, seg_of, size_by_rank);
   LAUNCH(c, rg_keep_flags_kernel, div_up(n, 256), 256, 0, size_by_rank, n, (u32)max(p->min_cluster_size, 0),
          (u32)max(p->max_cluster_size, 0), keep, sc + 61);
   CHECK_LAUNCH(c);
