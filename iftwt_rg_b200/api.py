@@ -16,7 +16,7 @@ from . import _build
 
 IFTWT_MAX_COST = 500
 
-STAGES = ("upload", "grid", "knn", "graph", "normals", "seeds", "ift", "download")
+STAGES = ("upload", "grid", "knn", "graph", "normals", "seeds", "ift", "download", "knn_cell")
 
 
 class IftwtError(RuntimeError):

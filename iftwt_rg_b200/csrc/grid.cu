@@ -103,17 +103,42 @@ __global__ void fine_key_kernel(const float4* __restrict__ pts, u32 n, double ox
   keys[i] = morton3(ix, iy, iz);
 }
 
-// hist[m] = number of adjacent sorted keys whose highest differing bit triple is m
-__global__ void level_hist_kernel(const u64* __restrict__ keys, u32 n, u32* __restrict__ hist) {
-  __shared__ u32 sh[16];
-  if (threadIdx.x < 16) sh[threadIdx.x] = 0;
+__device__ __forceinline__ u32 lower_bound_keys(const u64* __restrict__ a, u32 n, u64 v) {
+  u32 lo = 0, hi = n;
+  while (lo < hi) {
+    u32 mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+// Point-weighted cell occupancy at every octree level of the bounding cube: for a
+// sample of points, the number of points sharing their level-l cell (a Morton-prefix
+// range of the sorted keys).  Unlike N / #occupied cells this is not dragged down by
+// the partially filled cells along surface boundaries, so it measures the density a
+// query actually sees.  sums[l] accumulates the run lengths, l = 0..16.
+__global__ void occupancy_kernel(const u64* __restrict__ keys, u32 n, u32 stride, u32 n_samples,
+                                 unsigned long long* __restrict__ sums) {
+  __shared__ unsigned long long sh[17];
+  if (threadIdx.x < 17) sh[threadIdx.x] = 0ull;
   __syncthreads();
-  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x + 1; i < n; i += gridDim.x * blockDim.x) {
-    u64 x = keys[i] ^ keys[i - 1];
-    if (x) atomicAdd(&sh[(63 - __clzll((long long)x)) / 3], 1u);
+  u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n_samples) {
+    u64 key = keys[(size_t)s * stride];
+    u32 lo = 0, hi = n;
+    for (int l = 1; l <= 16; ++l) {
+      int sh_bits = 3 * (16 - l);
+      u64 pfx = key >> sh_bits;
+      // the level-l range nests inside the level-(l-1) range
+      u32 a = lo + lower_bound_keys(keys + lo, hi - lo, pfx << sh_bits);
+      u32 b = lo + lower_bound_keys(keys + lo, hi - lo, (pfx + 1) << sh_bits);
+      lo = a;
+      hi = b;
+      atomicAdd(&sh[l], (unsigned long long)(hi - lo));
+    }
   }
   __syncthreads();
-  if (threadIdx.x < 16 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+  if (threadIdx.x >= 1 && threadIdx.x < 17 && sh[threadIdx.x]) atomicAdd(&sums[threadIdx.x], sh[threadIdx.x]);
 }
 
 __global__ void cell_key_kernel(const float4* __restrict__ pts, u32 n, double ox, double oy, double oz,
@@ -195,8 +220,8 @@ int grid_build(iftwt_ctx* c, int k) {
   // --- bounding box ---
   hs[0] = hs[1] = hs[2] = 0x7FFFFFFF;
   hs[3] = hs[4] = hs[5] = (int)0x80000000;
-  for (int i = 6; i < 64; ++i) hs[i] = 0;
-  CU_TRY(c, cudaMemcpyAsync(sc, hs, 64 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  for (int i = 6; i < 128; ++i) hs[i] = 0;
+  CU_TRY(c, cudaMemcpyAsync(sc, hs, 128 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   LAUNCH(c, bbox_kernel, c->sm_count * 8, 256, 0, pts, n, sc);
   CHECK_LAUNCH(c);
   CU_TRY(c, cudaMemcpyAsync(hs, sc, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -226,20 +251,22 @@ int grid_build(iftwt_ctx* c, int k) {
     ENSURE(c, c->tmp, tb);
     CU_TRY(c, cub::DeviceRadixSort::SortKeys(c->tmp.p, tb, k0, k1, (int)n, 0, 48, c->stream));
     c->stats.kernel_launches += 8;  // CUB onesweep: histogram + 6 passes (+ scan)
-    u32* hist = (u32*)(sc + 16);
-    LAUNCH(c, level_hist_kernel, c->sm_count * 4, 256, 0, k1, n, hist);
+    unsigned long long* sums = (unsigned long long*)(sc + 80);  // 17 x u64, 8-byte aligned
+    u32 stride = n / 65536u;
+    if (stride == 0) stride = 1;
+    u32 n_samples = (n + stride - 1) / stride;
+    LAUNCH(c, occupancy_kernel, div_up(n_samples, 128), 128, 0, k1, n, stride, n_samples, sums);
     CHECK_LAUNCH(c);
-    CU_TRY(c, cudaMemcpyAsync(hs + 16, hist, 16 * sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(hs + 80, sums, 17 * 8, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
-    const u32* hh = (const u32*)(hs + 16);
+    const unsigned long long* hh = (const unsigned long long*)(hs + 80);
     double ppc[17];
-    for (int l = 0; l <= 16; ++l) {
-      double occ = 1.0;
-      for (int m = 16 - l; m <= 15; ++m) occ += hh[m];
-      ppc[l] = (double)n / occ;
-    }
-    const double beta = env_double("IFTWT_PPC_PER_K", 0.55);
-    double target = beta * (double)(k < 2 ? 2 : k);
+    ppc[0] = (double)n;
+    for (int l = 1; l <= 16; ++l) ppc[l] = fmax(1.0, (double)hh[l] / (double)n_samples);
+    // a Poisson-filled cell of mean occupancy m is seen by its own points as m + 1;
+    // m = 0.54 k puts the k-th neighbour at cell / 1.3 on a surface
+    const double beta = env_double("IFTWT_PPC_PER_K", 0.54);
+    double target = beta * (double)(k < 2 ? 2 : k) + 1.0;
     if (ppc[0] <= target) {
       cell = side;
     } else {

@@ -393,6 +393,7 @@ int knn_run(iftwt_ctx* c, int k) {
   float tau0 = (float)(g.cell * g.cell * 0.6);
   const float4* spts = c->spts.as<float4>();
   unsigned blocks = div_up(g.n_cells, KNN_WARPS);
+  cudaEventRecord(c->ev0[IFTWT_STAGE_KNN_CELL], c->stream);
   if (k <= 32) {
     size_t sm = cell_kernel_smem(2);
     CU_TRY(c, cudaFuncSetAttribute(knn_cell_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -404,6 +405,8 @@ int knn_run(iftwt_ctx* c, int k) {
     LAUNCH(c, knn_cell_kernel<4>, blocks, KNN_WARPS * 32, sm, g, spts, c->qb2.as<float>(), k, tau0,
            c->nbr.as<u32>(), c->nd2.as<float>(), c->kth.as<u64>(), c->fb_list.as<u32>(), fb_count);
   }
+  cudaEventRecord(c->ev1[IFTWT_STAGE_KNN_CELL], c->stream);
+  c->ev_set[IFTWT_STAGE_KNN_CELL] = true;
   CHECK_LAUNCH(c);
   unsigned gblocks = c->sm_count * 8;
   {

@@ -61,13 +61,16 @@ __device__ __forceinline__ bool smooth_pass(const float4 nu, const float4 nv, fl
   return !(dp < cos_thr);  // NaN passes, as in PCL
 }
 
-__global__ void rank_keys_kernel(const float4* __restrict__ nrm, const float4* __restrict__ spts, u32 n,
-                                 u64* __restrict__ keys, u32* __restrict__ vals, u32* __restrict__ parent) {
-  u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  keys[j] = ((u64)__float_as_uint(nrm[j].w) << 32) | (u64)__float_as_uint(spts[j].w);
-  vals[j] = j;
-  parent[j] = j;
+// keys in ORIGINAL order so that a stable 32-bit sort on the curvature bits breaks
+// ties by ascending original index: the canonical (curvature, index) order
+__global__ void rank_keys_kernel(const float4* __restrict__ nrm, const u32* __restrict__ inv, u32 n,
+                                 u32* __restrict__ keys, u32* __restrict__ vals, u32* __restrict__ parent) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u32 j = inv[i];
+  keys[i] = __float_as_uint(nrm[j].w);
+  vals[i] = j;
+  parent[i] = i;
 }
 __global__ void scatter_rank_kernel(const u32* __restrict__ sorted_vals, u32 n, u32* __restrict__ rank) {
   u32 r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -75,49 +78,68 @@ __global__ void scatter_rank_kernel(const u32* __restrict__ sorted_vals, u32 n, 
   rank[sorted_vals[r]] = r;
 }
 
-// pass 0: union mutual smooth arcs, count one-way smooth arcs.  pass 1: also emit them.
-__global__ void rg_arcs_kernel(const u32* __restrict__ nbr, const float* __restrict__ nd2,
-                               const u64* __restrict__ kth, const float4* __restrict__ spts,
-                               const float4* __restrict__ nrm, size_t n_entries, int k, float cos_thr,
-                               u32* __restrict__ parent, int pass, u32* __restrict__ counter,
-                               u32* __restrict__ arc_u, u32* __restrict__ arc_v) {
-  size_t a = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+// One pass over the arcs: union the mutual smooth ones, append the one-way smooth
+// ones to (arc_u, arc_v).  The append is aggregated per block (one global atomic per
+// block, not per warp: 10^7 same-address atomics cost more than the kernel itself).
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+rg_arcs_kernel(const u32* __restrict__ nbr, const float* __restrict__ nd2, const u64* __restrict__ kth,
+               const float4* __restrict__ spts, const float4* __restrict__ nrm, size_t n_entries, int k,
+               float cos_thr, u32* __restrict__ parent, u32* __restrict__ counter, u32* __restrict__ arc_u,
+               u32* __restrict__ arc_v) {
+  __shared__ u32 s_warp[8];
+  __shared__ u32 s_base;
+  const size_t a = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   bool oneway = false;
   u32 u = 0, v = 0;
   if (a < n_entries) {
-    u = (u32)(a / k);
+    u = (u32)((IdxT)a / (IdxT)k);
     v = nbr[a];
     if (v != SID_NONE && v != u && smooth_pass(nrm[u], nrm[v], cos_thr)) {
       u64 key = ((u64)__float_as_uint(nd2[a]) << 32) | (u64)__float_as_uint(spts[u].w);
       if (key <= kth[v]) {
-        if (pass == 0 && u > v) uf_union(parent, u, v);  // the twin arc v->u does the same union
+        if (u > v) uf_union(parent, u, v);  // the twin arc v->u would do the same union
       } else {
         oneway = true;
       }
     }
   }
-  unsigned m = __ballot_sync(0xffffffffu, oneway);
-  if (m == 0) return;
-  int lane = threadIdx.x & 31;
-  u32 base = 0;
-  if (lane == 0) base = atomicAdd(counter, (u32)__popc(m));
-  base = __shfl_sync(0xffffffffu, base, 0);
-  if (oneway && pass == 1) {
-    u32 p = base + __popc(m & ((1u << lane) - 1u));
+  const unsigned m = __ballot_sync(0xffffffffu, oneway);
+  if (lane == 0) s_warp[warp] = (u32)__popc(m);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    u32 tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      u32 c = s_warp[w];
+      s_warp[w] = tot;
+      tot += c;
+    }
+    s_base = tot ? atomicAdd(counter, tot) : 0u;
+  }
+  __syncthreads();
+  if (oneway) {
+    u32 p = s_base + s_warp[warp] + (u32)__popc(m & ((1u << lane) - 1u));
     arc_u[p] = u;
     arc_v[p] = v;
   }
 }
 
 // root[] is a separate array: writing the root back into parent[] would race with
-// the path halving of concurrent finds, which may overwrite it with a non-root ancestor
+// the path halving of concurrent finds, which may overwrite it with a non-root ancestor.
+// Lanes that share a root (spatial neighbours mostly do) combine before the atomic.
 __global__ void rg_flatten_kernel(u32* __restrict__ parent, const u32* __restrict__ rank, u32 n,
                                   u32* __restrict__ root, u32* __restrict__ L) {
   u32 v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= n) return;
+  const bool valid = v < n;
+  const unsigned act = __ballot_sync(0xffffffffu, valid);
+  if (!valid) return;
   u32 r = uf_find(parent, v);
   root[v] = r;
-  atomicMin(&L[r], rank[v]);
+  const unsigned grp = __match_any_sync(act, r);
+  const u32 mn = __reduce_min_sync(grp, rank[v]);
+  if ((int)(threadIdx.x & 31) == __ffs(grp) - 1 && mn < *(volatile u32*)&L[r]) atomicMin(&L[r], mn);
 }
 // arcs to root space
 __global__ void rg_arcs_to_roots_kernel(const u32* __restrict__ root, u32 m, u32* __restrict__ arc_u,
@@ -139,14 +161,17 @@ __global__ void rg_sweep_kernel(const u32* __restrict__ arc_u, const u32* __rest
     *changed = 1u;
   }
 }
-// per point: segment = L[root]; count sizes by seed rank
+// per point: segment = L[root]; count sizes by seed rank (warp-aggregated)
 __global__ void rg_sizes_kernel(const u32* __restrict__ root, const u32* __restrict__ L, u32 n,
                                 u32* __restrict__ seg_of, u32* __restrict__ size_by_rank) {
   u32 v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= n) return;
+  const bool valid = v < n;
+  const unsigned act = __ballot_sync(0xffffffffu, valid);
+  if (!valid) return;
   u32 s = L[root[v]];
   seg_of[v] = s;
-  atomicAdd(&size_by_rank[s], 1u);
+  const unsigned grp = __match_any_sync(act, s);
+  if ((int)(threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(&size_by_rank[s], (u32)__popc(grp));
 }
 __global__ void rg_keep_flags_kernel(const u32* __restrict__ size_by_rank, u32 n, u32 min_sz, u32 max_sz,
                                      u32* __restrict__ keep, u32* __restrict__ nseg) {
@@ -164,20 +189,23 @@ __global__ void rg_kept_sizes_kernel(const u32* __restrict__ size_by_rank, const
   if (r >= n || !keep[r]) return;
   ksize[kept_id[r]] = size_by_rank[r];
 }
-// member keys in ORIGINAL order: (kept cluster << 32 | original index) or ~0
+// members in ORIGINAL order: key = kept cluster (n_kept for dropped points), value =
+// original index; a stable sort on the key groups clusters with ascending indices
 __global__ void rg_member_keys_kernel(const u32* __restrict__ seg_of, const u32* __restrict__ keep,
                                       const u32* __restrict__ kept_id, const u32* __restrict__ inv, u32 n,
-                                      u64* __restrict__ keys, int* __restrict__ point_label) {
+                                      u32 n_kept, u32* __restrict__ keys, u32* __restrict__ vals,
+                                      int* __restrict__ point_label) {
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   u32 s = seg_of[inv[i]];
   bool kp = keep[s] != 0;
-  u32 c = kp ? kept_id[s] : 0u;
-  keys[i] = kp ? (((u64)c << 32) | (u64)i) : 0xFFFFFFFFFFFFFFFFull;
+  u32 c = kp ? kept_id[s] : n_kept;
+  keys[i] = c;
+  vals[i] = i;
   point_label[i] = kp ? (int)c : -1;
 }
 // one thread per kept cluster: pcl::compute3DCentroid, FP32, ascending point index
-__global__ void rg_centroid_kernel(const u64* __restrict__ sorted_keys, const u32* __restrict__ kstart,
+__global__ void rg_centroid_kernel(const u32* __restrict__ members, const u32* __restrict__ kstart,
                                    const u32* __restrict__ ksize, u32 n_kept,
                                    const float4* __restrict__ pts_in, float4* __restrict__ centroid) {
   u32 c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -186,8 +214,7 @@ __global__ void rg_centroid_kernel(const u64* __restrict__ sorted_keys, const u3
   float sx = 0.f, sy = 0.f, sz = 0.f;
 #pragma unroll 8
   for (u32 t = 0; t < cnt; ++t) {
-    u32 i = (u32)sorted_keys[b + t];
-    float4 p = pts_in[i];
+    float4 p = pts_in[members[b + t]];
     sx += p.x;
     sy += p.y;
     sz += p.z;
@@ -244,41 +271,41 @@ int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p) {
   u32* keep = size_by_rank + n;
   u32* kept_id = keep + n;
   {
-    u64* k0 = c->keys.as<u64>();
-    u64* k1 = c->keys_alt.as<u64>();
+    u32* k0 = c->keys.as<u32>();
+    u32* k1 = c->keys_alt.as<u32>();
     u32* v0 = c->vals_alt.as<u32>();
     u32* v1 = seg_of;  // scratch
-    LAUNCH(c, rank_keys_kernel, div_up(n, 256), 256, 0, nrm, spts, n, k0, v0, parent);
+    LAUNCH(c, rank_keys_kernel, div_up(n, 256), 256, 0, nrm, c->inv.as<u32>(), n, k0, v0, parent);
     size_t tb = 0;
-    CU_TRY(c, cub::DeviceRadixSort::SortPairs(nullptr, tb, k0, k1, v0, v1, (int)n, 0, 64, c->stream));
+    CU_TRY(c, cub::DeviceRadixSort::SortPairs(nullptr, tb, k0, k1, v0, v1, (int)n, 0, 32, c->stream));
     ENSURE(c, c->tmp, tb);
-    CU_TRY(c, cub::DeviceRadixSort::SortPairs(c->tmp.p, tb, k0, k1, v0, v1, (int)n, 0, 64, c->stream));
-    c->stats.kernel_launches += 10;
+    CU_TRY(c, cub::DeviceRadixSort::SortPairs(c->tmp.p, tb, k0, k1, v0, v1, (int)n, 0, 32, c->stream));
+    c->stats.kernel_launches += 5;
     LAUNCH(c, scatter_rank_kernel, div_up(n, 256), 256, 0, v1, n, rank);
     CHECK_LAUNCH(c);
   }
-  // 2. mutual smooth arcs -> union-find; count one-way smooth arcs
+  // 2. mutual smooth arcs -> union-find; one-way smooth arcs -> list (worst-case capacity)
   u32* d_cnt = sc + 56;
   CU_TRY(c, cudaMemsetAsync(d_cnt, 0, 16, c->stream));
-  LAUNCH(c, rg_arcs_kernel, div_up(ne, 256), 256, 0, c->nbr.as<u32>(), c->nd2.as<float>(), c->kth.as<u64>(),
-         spts, nrm, ne, k, cos_thr, parent, 0, d_cnt, (u32*)nullptr, (u32*)nullptr);
+  ENSURE(c, c->rg_aux2, (ne + 1) * 8);
+  u32* arc_u = c->rg_aux2.as<u32>();
+  u32* arc_v = arc_u + (ne + 1);
+  if (ne < 0xFFFFFFFFull) {
+    LAUNCH(c, rg_arcs_kernel<u32>, div_up(ne, 256), 256, 0, c->nbr.as<u32>(), c->nd2.as<float>(),
+           c->kth.as<u64>(), spts, nrm, ne, k, cos_thr, parent, d_cnt, arc_u, arc_v);
+  } else {
+    LAUNCH(c, rg_arcs_kernel<u64>, div_up(ne, 256), 256, 0, c->nbr.as<u32>(), c->nd2.as<float>(),
+           c->kth.as<u64>(), spts, nrm, ne, k, cos_thr, parent, d_cnt, arc_u, arc_v);
+  }
   CHECK_LAUNCH(c);
   CU_TRY(c, cudaMemcpyAsync(hs + 56, d_cnt, 4, cudaMemcpyDeviceToHost, c->stream));
-  CU_TRY(c, cudaStreamSynchronize(c->stream));
-  const u32 n_oneway = hs[56];
-  ENSURE(c, c->rg_aux2, ((size_t)n_oneway + 1) * 8);
-  u32* arc_u = c->rg_aux2.as<u32>();
-  u32* arc_v = arc_u + (n_oneway + 1);
-  if (n_oneway) {
-    LAUNCH(c, rg_arcs_kernel, div_up(ne, 256), 256, 0, c->nbr.as<u32>(), c->nd2.as<float>(),
-           c->kth.as<u64>(), spts, nrm, ne, k, cos_thr, parent, 1, d_cnt + 1, arc_u, arc_v);
-    CHECK_LAUNCH(c);
-  }
   // 3. component min rank, then label-min over one-way arcs
   CU_TRY(c, cudaMemsetAsync(L, 0xFF, (size_t)n * 4, c->stream));
   u32* root = c->vals_alt.as<u32>();  // free again once the ranks are scattered
   LAUNCH(c, rg_flatten_kernel, div_up(n, 256), 256, 0, parent, rank, n, root, L);
   CHECK_LAUNCH(c);
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  const u32 n_oneway = hs[56];
   u64 sweeps = 0;
   if (n_oneway) {
     LAUNCH(c, rg_arcs_to_roots_kernel, div_up(n_oneway, 256), 256, 0, root, n_oneway, arc_u, arc_v);
@@ -318,25 +345,28 @@ int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p) {
   CU_TRY(c, cudaStreamSynchronize(c->stream));
   const u32 n_kept = hs[62] + hs[63];
   c->stats.rg_segments = hs[61];
-  // point labels (original order) + member keys
+  // point labels (original order) + member lists
   ENSURE(c, c->out_a, (size_t)n * 4);
   int* point_label = c->out_a.as<int>();
-  u64* mkeys = c->keys.as<u64>();
-  u64* mkeys_sorted = c->keys_alt.as<u64>();
-  LAUNCH(c, rg_member_keys_kernel, div_up(n, 256), 256, 0, seg_of, keep, kept_id, c->inv.as<u32>(), n, mkeys,
-         point_label);
+  u32* mkeys = c->keys.as<u32>();
+  u32* mkeys_sorted = c->keys_alt.as<u32>();
+  u32* mvals = c->keys.as<u32>() + n;          // keys / keys_alt hold 8 bytes per point
+  u32* members = c->keys_alt.as<u32>() + n;
+  LAUNCH(c, rg_member_keys_kernel, div_up(n, 256), 256, 0, seg_of, keep, kept_id, c->inv.as<u32>(), n, n_kept,
+         mkeys, mvals, point_label);
   CHECK_LAUNCH(c);
   c->n_seeds = n_kept;
   ENSURE(c, c->seeds, ((size_t)n_kept + 1) * 4);
   if (n_kept) {
     int kbits = 1;
-    while ((1u << kbits) < n_kept + 1) ++kbits;  // +1: the all-ones key of dropped points sorts last
+    while ((1u << kbits) < n_kept + 1) ++kbits;
     size_t tb = 0;
-    CU_TRY(c, cub::DeviceRadixSort::SortKeys(nullptr, tb, mkeys, mkeys_sorted, (int)n, 0, 64, c->stream));
+    CU_TRY(c, cub::DeviceRadixSort::SortPairs(nullptr, tb, mkeys, mkeys_sorted, mvals, members, (int)n, 0, kbits,
+                                              c->stream));
     ENSURE(c, c->tmp, tb);
-    CU_TRY(c, cub::DeviceRadixSort::SortKeys(c->tmp.p, tb, mkeys, mkeys_sorted, (int)n, 0, 64, c->stream));
-    c->stats.kernel_launches += 10;
-    (void)kbits;
+    CU_TRY(c, cub::DeviceRadixSort::SortPairs(c->tmp.p, tb, mkeys, mkeys_sorted, mvals, members, (int)n, 0, kbits,
+                                              c->stream));
+    c->stats.kernel_launches += 1 + (kbits + 7) / 8;
     // kept cluster sizes / starts
     ENSURE(c, c->out_b, ((size_t)n_kept + 1) * 4 * 3 + (size_t)n_kept * 16 + 64);
     u32* ksize = c->out_b.as<u32>();
@@ -349,7 +379,7 @@ int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p) {
     ENSURE(c, c->tmp, tb2);
     CU_TRY(c, cub::DeviceScan::ExclusiveSum(c->tmp.p, tb2, ksize, kstart, (int)n_kept, c->stream));
     c->stats.kernel_launches += 2;
-    LAUNCH(c, rg_centroid_kernel, div_up(n_kept, 64), 64, 0, mkeys_sorted, kstart, ksize, n_kept,
+    LAUNCH(c, rg_centroid_kernel, div_up(n_kept, 64), 64, 0, members, kstart, ksize, n_kept,
            c->pts_in.as<float4>(), centroid);
     CHECK_LAUNCH(c);
     // 5. snap to the nearest input point

@@ -84,7 +84,8 @@ enum {
   IFTWT_STAGE_SEEDS = 5,   /* region growing, centroids, snap                  */
   IFTWT_STAGE_IFT = 6,     /* watershed                                        */
   IFTWT_STAGE_DOWNLOAD = 7,
-  IFTWT_STAGE_COUNT = 8
+  IFTWT_STAGE_KNN_CELL = 8, /* the k-NN fast-path kernel alone (the roofline kernel)     */
+  IFTWT_STAGE_COUNT = 9
 };
 
 typedef struct iftwt_stats {
