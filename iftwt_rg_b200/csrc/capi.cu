@@ -134,7 +134,8 @@ void iftwt_destroy(iftwt_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->pts_in, &c->stage_in, &c->spts, &c->perm, &c->inv, &c->keys, &c->keys_alt, &c->vals_alt,
                     &c->tmp, &c->scalars, &c->cell_key, &c->cell_cnt, &c->cell_start, &c->hkeys, &c->hvals,
-                    &c->qb2, &c->nbr, &c->nd2, &c->kth, &c->fb_list, &c->g_off, &c->g_adj, &c->g_deg, &c->nrm,
+                    &c->qb2, &c->nbr, &c->nd2, &c->kth, &c->fb_list, &c->g_off, &c->g_adj, &c->g_deg, &c->g_fwd,
+                    &c->ow_mask, &c->nrm,
                     &c->rg_rank, &c->rg_parent, &c->rg_label, &c->rg_aux, &c->rg_aux2, &c->seeds, &c->ift_state,
                     &c->ift_parent, &c->ift_w, &c->ift_byw, &c->ift_local, &c->out_a, &c->out_b};
   for (DevBuf* b : bufs)
@@ -153,11 +154,14 @@ static void invalidate(iftwt_ctx* c) {
   c->grid_k = 0;
   c->knn_k = 0;
   c->graph_k = 0;
+  c->graph_shares_nbr = false;
+  c->mask_k = 0;
   c->nrm_k = 0;
   c->seeds_valid = false;
   c->ift_valid = false;
   c->n_seeds = 0;
   c->n_arcs = 0;
+  c->n_rev = 0;
 }
 
 int iftwt_set_cloud(iftwt_ctx* c, const void* points, size_t stride, size_t n, int xyz_off, int i_off) {

@@ -68,8 +68,13 @@ struct iftwt_ctx {
   DevBuf fb_list;  // u32 [n] fallback query list
   // --- graph ---
   int graph_k = 0;
-  size_t n_arcs = 0;
-  DevBuf g_off, g_adj, g_deg;
+  size_t n_arcs = 0;         // forward (valid, non-self) + reverse arcs
+  size_t n_rev = 0;
+  bool graph_shares_nbr = false;  // forward rows alias `nbr` (else they live in g_fwd)
+  DevBuf g_off, g_adj, g_deg;     // reverse-arc CSR: offsets, targets, degree / fill cursor
+  DevBuf g_fwd;                   // private copy of the forward rows once nbr is recomputed
+  int mask_k = 0;                 // ow_mask describes the current k-NN lists when == knn_k
+  DevBuf ow_mask;                 // u64 [n] bit j: arc u -> nbr[u][j] is one-way
   // --- normals ---
   int nrm_k = 0;
   DevBuf nrm;  // float4 [n] sorted space {nx,ny,nz,curv}
@@ -132,6 +137,8 @@ int grid_build(iftwt_ctx* c, int k);                                       // gr
 int knn_run(iftwt_ctx* c, int k);                                          // knn.cu
 int knn_query_run(iftwt_ctx* c, const float4* d_q, size_t m, int k, u32* d_idx_sorted, float* d_d2);  // knn.cu
 int graph_build(iftwt_ctx* c);                                             // graph.cu
+int knn_mutual_run(iftwt_ctx* c, bool for_graph);
+int graph_detach_rows(iftwt_ctx* c);
 int graph_export(iftwt_ctx* c, u32* h_off, u32* h_adj, size_t cap, size_t* n_arcs);
 int normals_run(iftwt_ctx* c);                                             // normals.cu
 int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p);                     // seeds.cu

@@ -1,74 +1,107 @@
-// graph.cu — symmetric k-NN graph as CSR (graph builder (B), SURVEY finding 3).
+// graph.cu — symmetric k-NN graph (graph builder (B), SURVEY finding 3).
 //
 // Stands in for Graph::initialize / getAdjacencyList (graph.hpp:293-308, 63-66)
 // on the BASELINE k-NN configurations: vertices are the cloud points, u ~ v iff
-// v is among the k nearest neighbours of u or u among those of v.  The reverse
-// arcs are found without reading the neighbour's list: u is in kNN(v) exactly
-// when (d2(u,v), index(u)) <= the key of v's k-th neighbour, and d2 is bitwise
-// symmetric, so one 8-byte gather per arc decides mutuality.
+// v is among the k nearest neighbours of u or u among those of v.
+//
+// Device representation (sorted space), chosen so that the forward arcs are never
+// copied: adjacency(u) = the k-NN row of u (k entries, self / missing skipped at
+// read time) + a CSR list of the REVERSE arcs only (v with u in kNN(v) but v not
+// in kNN(u)).  The reverse arcs are found without reading the neighbour's list:
+// u is in kNN(v) exactly when (d2(u,v), index(u)) <= the key of v's k-th neighbour,
+// and d2 is bitwise symmetric, so one 8-byte gather per arc decides mutuality.  The
+// per-vertex bit mask of one-way arcs is kept: region growing reuses it.
+// The ascending, de-duplicated CSR in original indices is only materialised on
+// export (iftwt_knn_graph with host buffers).
 #include <cub/cub.cuh>
 
 #include "common.cuh"
 
 #define SID_NONE 0xFFFFFFFFu
 
-__device__ __forceinline__ bool arc_is_mutual(const float4* __restrict__ spts, const float* __restrict__ nd2,
-                                              const u64* __restrict__ kth, size_t arc, u32 u, u32 v) {
-  u64 key = ((u64)__float_as_uint(nd2[arc]) << 32) | (u64)__float_as_uint(spts[u].w);
-  return key <= kth[v];
+// One warp per vertex, lane j <-> arc j (two rounds when k > 32).
+//   ow_mask[u]  bit j set: arc u -> row[j] is one-way (u is not in kNN(row[j]))
+//   rdeg[v]    += 1 for every one-way arc into v          (when rdeg != NULL)
+//   n_fwd      += number of valid forward arcs            (block-aggregated)
+__global__ void __launch_bounds__(256)
+knn_mutual_kernel(const u32* __restrict__ nbr, const float* __restrict__ nd2, const u64* __restrict__ kth,
+                  const float4* __restrict__ spts, u32 n, int k, u64* __restrict__ ow_mask,
+                  u32* __restrict__ rdeg, unsigned long long* __restrict__ n_fwd) {
+  __shared__ u32 s_cnt[8];
+  const u32 u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  u32 valid_cnt = 0;
+  if (u < n) {
+    const u32 ou = __float_as_uint(spts[u].w);
+    u64 mask = 0;
+    for (int base = 0; base < k; base += 32) {
+      const int j = base + lane;
+      bool valid = false, oneway = false;
+      u32 v = SID_NONE;
+      if (j < k) {
+        v = nbr[(size_t)u * k + j];
+        valid = v != SID_NONE && v != u;
+        if (valid) {
+          u64 key = ((u64)__float_as_uint(nd2[(size_t)u * k + j]) << 32) | (u64)ou;
+          oneway = key > kth[v];
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, oneway);
+      valid_cnt += (u32)__popc(__ballot_sync(0xffffffffu, valid));
+      mask |= (u64)m << base;
+      if (oneway && rdeg) atomicAdd(&rdeg[v], 1u);
+    }
+    if (lane == 0) ow_mask[u] = mask;
+  }
+  if (n_fwd) {
+    if (lane == 0) s_cnt[warp] = valid_cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      u32 t = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += s_cnt[w];
+      if (t) atomicAdd(n_fwd, (unsigned long long)t);
+    }
+  }
 }
 
-// forward degree: valid, non-self entries of the row
-__global__ void graph_fwd_degree_kernel(const u32* __restrict__ nbr, u32 n, int k, u32* __restrict__ fdeg,
-                                        u32* __restrict__ deg) {
-  u32 u = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per vertex: scatter the one-way arcs u -> v into v's reverse list
+__global__ void __launch_bounds__(256)
+graph_fill_rev_kernel(const u32* __restrict__ nbr, const u64* __restrict__ ow_mask, u32 n, int k,
+                      const u32* __restrict__ roff, u32* __restrict__ cursor, u32* __restrict__ radj) {
+  const u32 u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (u >= n) return;
-  u32 c = 0;
-  for (int j = 0; j < k; ++j) {
-    u32 v = nbr[(size_t)u * k + j];
-    c += (v != SID_NONE && v != u) ? 1u : 0u;
-  }
-  fdeg[u] = c;
-  deg[u] = c;
-}
-
-// one thread per (u, j): a one-way arc u->v adds a reverse entry to v's row
-__global__ void graph_rev_count_kernel(const u32* __restrict__ nbr, const float* __restrict__ nd2,
-                                       const u64* __restrict__ kth, const float4* __restrict__ spts,
-                                       size_t n_entries, int k, u32* __restrict__ deg) {
-  size_t a = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= n_entries) return;
-  u32 u = (u32)(a / k);
-  u32 v = nbr[a];
-  if (v == SID_NONE || v == u) return;
-  if (!arc_is_mutual(spts, nd2, kth, a, u, v)) atomicAdd(&deg[v], 1u);
-}
-
-__global__ void graph_fill_fwd_kernel(const u32* __restrict__ nbr, u32 n, int k, const u32* __restrict__ off,
-                                      u32* __restrict__ adj) {
-  u32 u = blockIdx.x * blockDim.x + threadIdx.x;
-  if (u >= n) return;
-  u32 o = off[u];
-  for (int j = 0; j < k; ++j) {
-    u32 v = nbr[(size_t)u * k + j];
-    if (v != SID_NONE && v != u) adj[o++] = v;
+  const u64 mask = ow_mask[u];
+  if (mask == 0) return;
+  for (int base = 0; base < k; base += 32) {
+    const int j = base + lane;
+    if (j < k && ((mask >> j) & 1ull)) {
+      u32 v = nbr[(size_t)u * k + j];
+      u32 p = atomicAdd(&cursor[v], 1u);
+      radj[roff[v] + p] = u;
+    }
   }
 }
 
-__global__ void graph_fill_rev_kernel(const u32* __restrict__ nbr, const float* __restrict__ nd2,
-                                      const u64* __restrict__ kth, const float4* __restrict__ spts,
-                                      size_t n_entries, int k, const u32* __restrict__ off,
-                                      const u32* __restrict__ fdeg, u32* __restrict__ cursor,
-                                      u32* __restrict__ adj) {
-  size_t a = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= n_entries) return;
-  u32 u = (u32)(a / k);
-  u32 v = nbr[a];
-  if (v == SID_NONE || v == u) return;
-  if (!arc_is_mutual(spts, nd2, kth, a, u, v)) {
-    u32 p = atomicAdd(&cursor[v], 1u);
-    adj[off[v] + fdeg[v] + p] = u;
+int knn_mutual_run(iftwt_ctx* c, bool for_graph) {
+  const u32 n = (u32)c->n;
+  const int k = c->knn_k;
+  ENSURE(c, c->ow_mask, (size_t)n * 8);
+  u32* rdeg = nullptr;
+  unsigned long long* d_nfwd = nullptr;
+  if (for_graph) {
+    ENSURE(c, c->g_deg, ((size_t)n + 1) * 4);
+    rdeg = c->g_deg.as<u32>();
+    CU_TRY(c, cudaMemsetAsync(rdeg, 0, ((size_t)n + 1) * 4, c->stream));
+    d_nfwd = (unsigned long long*)(c->scalars.as<int>() + 52);
+    CU_TRY(c, cudaMemsetAsync(d_nfwd, 0, 8, c->stream));
   }
+  LAUNCH(c, knn_mutual_kernel, div_up((size_t)n * 32, 256), 256, 0, c->nbr.as<u32>(), c->nd2.as<float>(),
+         c->kth.as<u64>(), c->spts.as<float4>(), n, k, c->ow_mask.as<u64>(), rdeg, d_nfwd);
+  CHECK_LAUNCH(c);
+  c->mask_k = k;
+  return IFTWT_OK;
 }
 
 int graph_build(iftwt_ctx* c) {
@@ -77,75 +110,101 @@ int graph_build(iftwt_ctx* c) {
   StageTimer st(c, IFTWT_STAGE_GRAPH);
   const u32 n = (u32)c->n;
   const int k = c->knn_k;
-  const size_t ne = (size_t)n * k;
-  ENSURE(c, c->g_deg, ((size_t)n + 1) * 4 * 2);  // [0..n] total degree / cursor, [n+1..] forward degree
+  TRY(knn_mutual_run(c, true));
   ENSURE(c, c->g_off, ((size_t)n + 1) * 4);
-  u32* deg = c->g_deg.as<u32>();
-  u32* fdeg = deg + (n + 1);
-  u32* off = c->g_off.as<u32>();
-  const u32* nbr = c->nbr.as<u32>();
-  const float* nd2 = c->nd2.as<float>();
-  const u64* kth = c->kth.as<u64>();
-  const float4* spts = c->spts.as<float4>();
-  CU_TRY(c, cudaMemsetAsync(deg + n, 0, 4, c->stream));
-  LAUNCH(c, graph_fwd_degree_kernel, div_up(n, 256), 256, 0, nbr, n, k, fdeg, deg);
-  LAUNCH(c, graph_rev_count_kernel, div_up(ne, 256), 256, 0, nbr, nd2, kth, spts, ne, k, deg);
-  CHECK_LAUNCH(c);
+  u32* rdeg = c->g_deg.as<u32>();
+  u32* roff = c->g_off.as<u32>();
   {
     size_t tb = 0;
-    CU_TRY(c, cub::DeviceScan::ExclusiveSum(nullptr, tb, deg, off, (int)(n + 1), c->stream));
+    CU_TRY(c, cub::DeviceScan::ExclusiveSum(nullptr, tb, rdeg, roff, (int)(n + 1), c->stream));
     ENSURE(c, c->tmp, tb);
-    CU_TRY(c, cub::DeviceScan::ExclusiveSum(c->tmp.p, tb, deg, off, (int)(n + 1), c->stream));
+    CU_TRY(c, cub::DeviceScan::ExclusiveSum(c->tmp.p, tb, rdeg, roff, (int)(n + 1), c->stream));
     c->stats.kernel_launches += 2;
   }
   u32* hs = (u32*)c->h_scalars;
-  CU_TRY(c, cudaMemcpyAsync(hs + 52, off + n, 4, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(hs + 54, roff + n, 4, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(hs + 52, c->scalars.as<int>() + 52, 8, cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(c, cudaStreamSynchronize(c->stream));
-  const size_t arcs = hs[52];
-  ENSURE(c, c->g_adj, (arcs + 1) * 4);
-  CU_TRY(c, cudaMemsetAsync(deg, 0, (size_t)n * 4, c->stream));  // now the reverse-fill cursor
-  LAUNCH(c, graph_fill_fwd_kernel, div_up(n, 256), 256, 0, nbr, n, k, off, c->g_adj.as<u32>());
-  LAUNCH(c, graph_fill_rev_kernel, div_up(ne, 256), 256, 0, nbr, nd2, kth, spts, ne, k, off, fdeg, deg,
-         c->g_adj.as<u32>());
-  CHECK_LAUNCH(c);
-  c->n_arcs = arcs;
+  const size_t n_rev = hs[54];
+  const size_t n_fwd = *(unsigned long long*)(hs + 52);
+  ENSURE(c, c->g_adj, (n_rev + 1) * 4);
+  CU_TRY(c, cudaMemsetAsync(rdeg, 0, (size_t)n * 4, c->stream));  // now the fill cursor
+  if (n_rev) {
+    LAUNCH(c, graph_fill_rev_kernel, div_up((size_t)n * 32, 256), 256, 0, c->nbr.as<u32>(), c->ow_mask.as<u64>(),
+           n, k, roff, rdeg, c->g_adj.as<u32>());
+    CHECK_LAUNCH(c);
+  }
+  c->n_rev = n_rev;
+  c->n_arcs = n_fwd + n_rev;
   c->graph_k = k;
-  c->stats.n_arcs = arcs;
+  c->graph_shares_nbr = true;
+  c->stats.n_arcs = c->n_arcs;
   c->ift_valid = false;
   return IFTWT_OK;
 }
 
+// the k-NN lists are about to be overwritten with another k: keep the graph's rows
+int graph_detach_rows(iftwt_ctx* c) {
+  if (c->graph_k == 0 || !c->graph_shares_nbr) return IFTWT_OK;
+  const size_t bytes = c->n * (size_t)c->graph_k * 4;
+  ENSURE(c, c->g_fwd, bytes);
+  CU_TRY(c, cudaMemcpyAsync(c->g_fwd.p, c->nbr.p, bytes, cudaMemcpyDeviceToDevice, c->stream));
+  c->graph_shares_nbr = false;
+  return IFTWT_OK;
+}
+
 // ---- export in original index space, rows ascending ----
-__global__ void export_degree_kernel(const u32* __restrict__ off, const u32* __restrict__ inv, u32 n,
-                                     u32* __restrict__ deg_o) {
-  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void export_degree_kernel(const u32* __restrict__ fwd, int k, const u32* __restrict__ roff,
+                                     const u32* __restrict__ inv, u32 n, u32* __restrict__ deg_o) {
+  const u32 i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (i > n) return;
   if (i == n) {
-    deg_o[i] = 0;
+    if (lane == 0) deg_o[i] = 0;
     return;
   }
-  u32 s = inv[i];
-  deg_o[i] = off[s + 1] - off[s];
+  const u32 s = inv[i];
+  u32 cnt = 0;
+  for (int base = 0; base < k; base += 32) {
+    int j = base + lane;
+    u32 v = j < k ? fwd[(size_t)s * k + j] : SID_NONE;
+    cnt += (u32)__popc(__ballot_sync(0xffffffffu, v != SID_NONE && v != s));
+  }
+  if (lane == 0) deg_o[i] = cnt + (roff[s + 1] - roff[s]);
 }
-__global__ void export_rows_kernel(const u32* __restrict__ off, const u32* __restrict__ adj,
-                                   const u32* __restrict__ inv, const u32* __restrict__ perm, u32 n,
-                                   const u32* __restrict__ off_o, u32* __restrict__ adj_o) {
-  u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (gw >= n) return;
-  u32 s = inv[gw];
-  u32 b = off[s], e = off[s + 1], o = off_o[gw];
-  for (u32 t = b + lane; t < e; t += 32) adj_o[o + (t - b)] = perm[adj[t]];
+__global__ void export_rows_kernel(const u32* __restrict__ fwd, int k, const u32* __restrict__ roff,
+                                   const u32* __restrict__ radj, const u32* __restrict__ inv,
+                                   const u32* __restrict__ perm, u32 n, const u32* __restrict__ off_o,
+                                   u32* __restrict__ adj_o) {
+  const u32 i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const u32 s = inv[i];
+  u32 o = off_o[i];
+  for (int base = 0; base < k; base += 32) {
+    int j = base + lane;
+    u32 v = j < k ? fwd[(size_t)s * k + j] : SID_NONE;
+    bool valid = v != SID_NONE && v != s;
+    unsigned m = __ballot_sync(0xffffffffu, valid);
+    if (valid) adj_o[o + __popc(m & ((1u << lane) - 1u))] = perm[v];
+    o += (u32)__popc(m);
+  }
+  const u32 b = roff[s], e = roff[s + 1];
+  for (u32 t = b + lane; t < e; t += 32) adj_o[o + (t - b)] = perm[radj[t]];
 }
 
 int graph_export(iftwt_ctx* c, u32* h_off, u32* h_adj, size_t cap, size_t* n_arcs) {
   const u32 n = (u32)c->n;
   const size_t arcs = c->n_arcs;
+  const int k = c->graph_k;
+  const u32* fwd = c->graph_shares_nbr ? c->nbr.as<u32>() : c->g_fwd.as<u32>();
   if (n_arcs) *n_arcs = arcs;
+  if (arcs >= 0xFFFFFFFFull) return ctx_fail(c, IFTWT_ERR_UNSUPPORTED, "graph too large for 32-bit CSR offsets");
   ENSURE(c, c->out_a, ((size_t)n + 1) * 4 * 2);
   u32* deg_o = c->out_a.as<u32>();
   u32* off_o = deg_o + (n + 1);
-  LAUNCH(c, export_degree_kernel, div_up((size_t)n + 1, 256), 256, 0, c->g_off.as<u32>(), c->inv.as<u32>(), n,
-         deg_o);
+  LAUNCH(c, export_degree_kernel, div_up(((size_t)n + 1) * 32, 256), 256, 0, fwd, k, c->g_off.as<u32>(),
+         c->inv.as<u32>(), n, deg_o);
   size_t tb = 0;
   CU_TRY(c, cub::DeviceScan::ExclusiveSum(nullptr, tb, deg_o, off_o, (int)(n + 1), c->stream));
   ENSURE(c, c->tmp, tb);
@@ -159,8 +218,8 @@ int graph_export(iftwt_ctx* c, u32* h_off, u32* h_adj, size_t cap, size_t* n_arc
     ENSURE(c, c->out_b, (arcs + 1) * 4 * 2);
     u32* tmp_adj = c->out_b.as<u32>();
     u32* srt_adj = tmp_adj + (arcs + 1);
-    LAUNCH(c, export_rows_kernel, div_up((size_t)n * 32, 256), 256, 0, c->g_off.as<u32>(), c->g_adj.as<u32>(),
-           c->inv.as<u32>(), c->perm.as<u32>(), n, off_o, tmp_adj);
+    LAUNCH(c, export_rows_kernel, div_up((size_t)n * 32, 256), 256, 0, fwd, k, c->g_off.as<u32>(),
+           c->g_adj.as<u32>(), c->inv.as<u32>(), c->perm.as<u32>(), n, off_o, tmp_adj);
     CHECK_LAUNCH(c);
     size_t tb2 = 0;
     CU_TRY(c, cub::DeviceSegmentedSort::SortKeys(nullptr, tb2, tmp_adj, srt_adj, (int)arcs, (int)n, off_o,

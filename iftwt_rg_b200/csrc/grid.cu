@@ -373,6 +373,8 @@ int grid_build(iftwt_ctx* c, int k) {
   // everything derived from an older grid is stale
   c->knn_k = 0;
   c->graph_k = 0;
+  c->graph_shares_nbr = false;
+  c->mask_k = 0;
   c->nrm_k = 0;
   c->seeds_valid = false;
   c->ift_valid = false;

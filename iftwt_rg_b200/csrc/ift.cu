@@ -108,12 +108,28 @@ __global__ void ift_segments_kernel(const unsigned short* __restrict__ w_sorted,
   seg_off[c] = lo;
 }
 
-// A: one warp per newly opened vertex
+// A: one warp per newly opened vertex.  adjacency(t) = its k-NN row + its reverse arcs.
+struct OpenCtx {
+  const unsigned short* w16;
+  const u64* state;
+  u32* parent;
+  u32 level;
+};
+__device__ __forceinline__ void ift_visit(const OpenCtx& x, u32 t, u32 u, u32& lmin) {
+  if ((u32)x.w16[u] > x.level) return;  // closed at this level
+  u32 ru = uf_find(x.parent, u);
+  u64 su = x.state[ru];
+  if ((u32)(su >> 32) < IFTWT_MAX_COST) {
+    lmin = min(lmin, (u32)su);  // conquered neighbour: an entry offer at cost `level`
+  } else {
+    uf_union_roots(x.parent, uf_find(x.parent, t), ru);
+  }
+}
 __global__ void __launch_bounds__(256)
 ift_level_open_kernel(const u32* __restrict__ byw, u32 seg_begin, u32 seg_len, u32 level,
-                      const u32* __restrict__ off, const u32* __restrict__ adj,
-                      const unsigned short* __restrict__ w16, const u64* __restrict__ state,
-                      u32* __restrict__ parent, u32* __restrict__ local_min) {
+                      const u32* __restrict__ fwd, int k, const u32* __restrict__ roff,
+                      const u32* __restrict__ radj, const unsigned short* __restrict__ w16,
+                      const u64* __restrict__ state, u32* __restrict__ parent, u32* __restrict__ local_min) {
   const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (gw >= seg_len) return;
@@ -122,19 +138,14 @@ ift_level_open_kernel(const u32* __restrict__ byw, u32 seg_begin, u32 seg_len, u
     if (lane == 0) local_min[t] = LBL_NONE;
     return;
   }
+  OpenCtx x{w16, state, parent, level};
   u32 lmin = LBL_NONE;
-  const u32 b = off[t], e = off[t + 1];
-  for (u32 a = b + lane; a < e; a += 32) {
-    u32 u = adj[a];
-    if ((u32)w16[u] > level) continue;  // closed at this level
-    u32 ru = uf_find(parent, u);
-    u64 su = state[ru];
-    if ((u32)(su >> 32) < IFTWT_MAX_COST) {
-      lmin = min(lmin, (u32)su);  // conquered neighbour: an entry offer at cost `level`
-    } else {
-      uf_union_roots(parent, uf_find(parent, t), ru);
-    }
+  for (int j = lane; j < k; j += 32) {
+    u32 u = fwd[(size_t)t * k + j];
+    if (u != 0xFFFFFFFFu && u != t) ift_visit(x, t, u, lmin);
   }
+  const u32 b = roff[t], e = roff[t + 1];
+  for (u32 a = b + lane; a < e; a += 32) ift_visit(x, t, radj[a], lmin);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
   if (lane == 0) local_min[t] = lmin;
@@ -214,13 +225,14 @@ int ift_run(iftwt_ctx* c, const float* d_w_orig, const u32* d_seeds_orig, size_t
     return ctx_fail(c, IFTWT_ERR_WEIGHTS, "%u IFT weights are negative, NaN or not integer valued", hs[64]);
   if (hs[65]) return ctx_fail(c, IFTWT_ERR_INVALID, "%u seed indices are out of range", hs[65]);
   const u32* seg = hs + 128;
+  const u32* fwd = c->graph_shares_nbr ? c->nbr.as<u32>() : c->g_fwd.as<u32>();
   u64 levels = 0;
   for (u32 lv = 0; lv < IFTWT_MAX_COST; ++lv) {
     u32 b = seg[lv], len = seg[lv + 1] - seg[lv];
     if (len == 0) continue;
     ++levels;
-    LAUNCH(c, ift_level_open_kernel, div_up((size_t)len * 32, 256), 256, 0, byw, b, len, lv, c->g_off.as<u32>(),
-           c->g_adj.as<u32>(), w16, state, parent, local_min);
+    LAUNCH(c, ift_level_open_kernel, div_up((size_t)len * 32, 256), 256, 0, byw, b, len, lv, fwd, c->graph_k,
+           c->g_off.as<u32>(), c->g_adj.as<u32>(), w16, state, parent, local_min);
     LAUNCH(c, ift_level_settle_kernel, div_up(len, 256), 256, 0, byw, b, len, lv, parent, local_min, state);
   }
   CHECK_LAUNCH(c);

@@ -381,6 +381,8 @@ int knn_run(iftwt_ctx* c, int k) {
   if (k < 1 || k > 64) return ctx_fail(c, IFTWT_ERR_INVALID, "k must be in [1, 64], got %d", k);
   TRY(grid_build(c, k));
   if (c->knn_k == k) return IFTWT_OK;
+  TRY(graph_detach_rows(c));  // the graph keeps its rows if they alias the lists we overwrite
+  c->mask_k = 0;
   StageTimer st(c, IFTWT_STAGE_KNN);
   const size_t n = c->n;
   ENSURE(c, c->nbr, n * k * 4);
@@ -418,7 +420,6 @@ int knn_run(iftwt_ctx* c, int k) {
   int* hs = (int*)c->h_scalars;
   CU_TRY(c, cudaMemcpyAsync(hs + 48, fb_count, 4, cudaMemcpyDeviceToHost, c->stream));
   c->knn_k = k;
-  c->graph_k = 0;
   return IFTWT_OK;
 }
 

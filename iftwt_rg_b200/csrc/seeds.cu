@@ -40,21 +40,6 @@ __device__ __forceinline__ u32 uf_find(u32* parent, u32 v) {
   }
   return v;
 }
-__device__ __forceinline__ void uf_union(u32* parent, u32 a, u32 b) {
-  u32 ra = uf_find(parent, a), rb = uf_find(parent, b);
-  while (ra != rb) {
-    if (ra < rb) {
-      u32 ret = atomicCAS(&parent[rb], rb, ra);
-      if (ret == rb) return;
-      rb = ret;
-    } else {
-      u32 ret = atomicCAS(&parent[ra], ra, rb);
-      if (ret == ra) return;
-      ra = ret;
-    }
-  }
-}
-
 // Eigen's unrolled 3-element reduction: e0 + (e1 + e2)   (oracle: dot3_eigen)
 __device__ __forceinline__ bool smooth_pass(const float4 nu, const float4 nv, float cos_thr) {
   float dp = fabsf(nv.x * nu.x + (nv.y * nu.y + nv.z * nu.z));
@@ -78,35 +63,61 @@ __global__ void scatter_rank_kernel(const u32* __restrict__ sorted_vals, u32 n, 
   rank[sorted_vals[r]] = r;
 }
 
-// One pass over the arcs: union the mutual smooth ones, append the one-way smooth
-// ones to (arc_u, arc_v).  The append is aggregated per block (one global atomic per
-// block, not per warp: 10^7 same-address atomics cost more than the kernel itself).
-template <typename IdxT>
+// One thread per vertex u (ECL-CC style): the smooth MUTUAL arcs to smaller ids are
+// hooked into the union-find with u's representative cached in a register; the smooth
+// ONE-WAY arcs are remembered in a bit mask and appended to (arc_u, arc_v) with one
+// global atomic per block.
 __global__ void __launch_bounds__(256)
-rg_arcs_kernel(const u32* __restrict__ nbr, const float* __restrict__ nd2, const u64* __restrict__ kth,
-               const float4* __restrict__ spts, const float4* __restrict__ nrm, size_t n_entries, int k,
-               float cos_thr, u32* __restrict__ parent, u32* __restrict__ counter, u32* __restrict__ arc_u,
-               u32* __restrict__ arc_v) {
+rg_arcs_kernel(const u32* __restrict__ nbr, const u64* __restrict__ ow_mask, const float4* __restrict__ nrm,
+               u32 n, int k, float cos_thr, u32* __restrict__ parent, u32* __restrict__ counter,
+               u32* __restrict__ arc_u, u32* __restrict__ arc_v) {
   __shared__ u32 s_warp[8];
   __shared__ u32 s_base;
-  const size_t a = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 u = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  bool oneway = false;
-  u32 u = 0, v = 0;
-  if (a < n_entries) {
-    u = (u32)((IdxT)a / (IdxT)k);
-    v = nbr[a];
-    if (v != SID_NONE && v != u && smooth_pass(nrm[u], nrm[v], cos_thr)) {
-      u64 key = ((u64)__float_as_uint(nd2[a]) << 32) | (u64)__float_as_uint(spts[u].w);
-      if (key <= kth[v]) {
-        if (u > v) uf_union(parent, u, v);  // the twin arc v->u would do the same union
+  u64 mask = 0;
+  if (u < n) {
+    const float4 nu = nrm[u];
+    const u64 ow = ow_mask[u];  // bit j: u is NOT among the k nearest of row[j] (graph.cu)
+    const u32* row = nbr + (size_t)u * k;
+    u32 ru = 0xFFFFFFFFu;
+    for (int j = 0; j < k; ++j) {
+      u32 v = row[j];
+      if (v == SID_NONE || v == u) continue;
+      if (!smooth_pass(nu, nrm[v], cos_thr)) continue;
+      if (!((ow >> j) & 1ull)) {
+        if (v < u) {  // the twin arc v->u is mutual and smooth too; one of the pair hooks
+          if (ru == 0xFFFFFFFFu) ru = uf_find(parent, u);
+          u32 rv = uf_find(parent, v);
+          while (ru != rv) {
+            if (ru < rv) {
+              u32 ret = atomicCAS(&parent[rv], rv, ru);
+              if (ret == rv) break;
+              rv = ret;
+            } else {
+              u32 ret = atomicCAS(&parent[ru], ru, rv);
+              if (ret == ru) {
+                ru = rv;
+                break;
+              }
+              ru = ret;
+            }
+          }
+        }
       } else {
-        oneway = true;
+        mask |= 1ull << j;
       }
     }
   }
-  const unsigned m = __ballot_sync(0xffffffffu, oneway);
-  if (lane == 0) s_warp[warp] = (u32)__popc(m);
+  // ---- block-aggregated append of the one-way arcs ----
+  u32 cnt = (u32)__popcll(mask);
+  u32 incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
   __syncthreads();
   if (threadIdx.x == 0) {
     u32 tot = 0;
@@ -119,10 +130,16 @@ rg_arcs_kernel(const u32* __restrict__ nbr, const float* __restrict__ nd2, const
     s_base = tot ? atomicAdd(counter, tot) : 0u;
   }
   __syncthreads();
-  if (oneway) {
-    u32 p = s_base + s_warp[warp] + (u32)__popc(m & ((1u << lane) - 1u));
-    arc_u[p] = u;
-    arc_v[p] = v;
+  if (mask) {
+    u32 p = s_base + s_warp[warp] + (incl - cnt);
+    const u32* row = nbr + (size_t)u * k;
+    while (mask) {
+      int j = __ffsll((long long)mask) - 1;
+      mask &= mask - 1;
+      arc_u[p] = u;
+      arc_v[p] = row[j];
+      ++p;
+    }
   }
 }
 
@@ -204,23 +221,32 @@ __global__ void rg_member_keys_kernel(const u32* __restrict__ seg_of, const u32*
   vals[i] = i;
   point_label[i] = kp ? (int)c : -1;
 }
-// one thread per kept cluster: pcl::compute3DCentroid, FP32, ascending point index
+// One warp per kept cluster: pcl::compute3DCentroid, FP32, ascending point index.
+// The 32 gathers of a batch are issued in parallel; the additions stay strictly
+// sequential (every lane carries the same running sums), so the result is the
+// literal left-to-right FP32 sum.
 __global__ void rg_centroid_kernel(const u32* __restrict__ members, const u32* __restrict__ kstart,
                                    const u32* __restrict__ ksize, u32 n_kept,
                                    const float4* __restrict__ pts_in, float4* __restrict__ centroid) {
-  u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (c >= n_kept) return;
-  u32 b = kstart[c], cnt = ksize[c];
+  const u32 b = kstart[c], cnt = ksize[c];
   float sx = 0.f, sy = 0.f, sz = 0.f;
-#pragma unroll 8
-  for (u32 t = 0; t < cnt; ++t) {
-    float4 p = pts_in[members[b + t]];
-    sx += p.x;
-    sy += p.y;
-    sz += p.z;
+  for (u32 base = 0; base < cnt; base += 32) {
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (base + lane < cnt) p = pts_in[members[b + base + lane]];
+    const int m = (int)min(32u, cnt - base);
+    for (int t = 0; t < m; ++t) {
+      sx += __shfl_sync(0xffffffffu, p.x, t);
+      sy += __shfl_sync(0xffffffffu, p.y, t);
+      sz += __shfl_sync(0xffffffffu, p.z, t);
+    }
   }
-  float d = (float)cnt;
-  centroid[c] = make_float4(sx / d, sy / d, sz / d, 0.f);
+  if (lane == 0) {
+    float d = (float)cnt;
+    centroid[c] = make_float4(sx / d, sy / d, sz / d, 0.f);
+  }
 }
 __global__ void rg_seed_ids_kernel(const u32* __restrict__ sid_sorted, const u32* __restrict__ perm, u32 m,
                                    u32* __restrict__ seeds) {
@@ -290,13 +316,9 @@ int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p) {
   ENSURE(c, c->rg_aux2, (ne + 1) * 8);
   u32* arc_u = c->rg_aux2.as<u32>();
   u32* arc_v = arc_u + (ne + 1);
-  if (ne < 0xFFFFFFFFull) {
-    LAUNCH(c, rg_arcs_kernel<u32>, div_up(ne, 256), 256, 0, c->nbr.as<u32>(), c->nd2.as<float>(),
-           c->kth.as<u64>(), spts, nrm, ne, k, cos_thr, parent, d_cnt, arc_u, arc_v);
-  } else {
-    LAUNCH(c, rg_arcs_kernel<u64>, div_up(ne, 256), 256, 0, c->nbr.as<u32>(), c->nd2.as<float>(),
-           c->kth.as<u64>(), spts, nrm, ne, k, cos_thr, parent, d_cnt, arc_u, arc_v);
-  }
+  if (c->mask_k != c->knn_k) TRY(knn_mutual_run(c, false));
+  LAUNCH(c, rg_arcs_kernel, div_up(n, 256), 256, 0, c->nbr.as<u32>(), c->ow_mask.as<u64>(), nrm, n, k, cos_thr,
+         parent, d_cnt, arc_u, arc_v);
   CHECK_LAUNCH(c);
   CU_TRY(c, cudaMemcpyAsync(hs + 56, d_cnt, 4, cudaMemcpyDeviceToHost, c->stream));
   // 3. component min rank, then label-min over one-way arcs
@@ -379,7 +401,7 @@ int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p) {
     ENSURE(c, c->tmp, tb2);
     CU_TRY(c, cub::DeviceScan::ExclusiveSum(c->tmp.p, tb2, ksize, kstart, (int)n_kept, c->stream));
     c->stats.kernel_launches += 2;
-    LAUNCH(c, rg_centroid_kernel, div_up(n_kept, 64), 64, 0, members, kstart, ksize, n_kept,
+    LAUNCH(c, rg_centroid_kernel, div_up((size_t)n_kept * 32, 128), 128, 0, members, kstart, ksize, n_kept,
            c->pts_in.as<float4>(), centroid);
     CHECK_LAUNCH(c);
     // 5. snap to the nearest input point
