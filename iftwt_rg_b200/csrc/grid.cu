@@ -264,8 +264,8 @@ int grid_build(iftwt_ctx* c, int k) {
     ppc[0] = (double)n;
     for (int l = 1; l <= 16; ++l) ppc[l] = fmax(1.0, (double)hh[l] / (double)n_samples);
     // a Poisson-filled cell of mean occupancy m is seen by its own points as m + 1;
-    // m = 0.54 k puts the k-th neighbour at cell / 1.3 on a surface
-    const double beta = env_double("IFTWT_PPC_PER_K", 0.54);
+    // m = 0.45 k puts the k-th neighbour at about cell / 1.2 on a surface (swept on B200)
+    const double beta = env_double("IFTWT_PPC_PER_K", 0.45);
     double target = beta * (double)(k < 2 ? 2 : k) + 1.0;
     if (ppc[0] <= target) {
       cell = side;

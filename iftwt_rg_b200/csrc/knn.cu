@@ -33,6 +33,170 @@ __device__ __forceinline__ u64 make_key(float d2, u32 orig) {
   return ((u64)__float_as_uint(d2) << 32) | (u64)orig;
 }
 
+struct CellWarp {  // per-warp shared-memory views + per-cell constants
+  const float4* s_pts;
+  const u32* s_id;
+  u32* s_d2;
+  u32* s_slot;
+  float* s_kd2;
+  int M;
+  u32 qs, qn, qoff;
+};
+
+__device__ __forceinline__ void count_lt(int& acc, u32 x, u32 key) {
+  // acc += (x < key) as one compare + one predicated add
+  asm("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(acc) : "r"(x), "r"(key));
+}
+
+// The queries of one cell.  RR = rounds of 32 staged candidates, compile-time so the
+// per-round code carries no branches; E = survivor slots per lane (CS = 32 E).
+template <int E, int RR>
+__device__ __forceinline__ void cell_queries(const CellWarp& w, const float* __restrict__ qb2, int k, float tau0,
+                                             u32* __restrict__ nbr, float* __restrict__ nd2,
+                                             u64* __restrict__ kth, u32* __restrict__ fb_list,
+                                             u32* __restrict__ fb_count, int lane) {
+  constexpr int CS = 32 * E;
+  const unsigned FULL = 0xffffffffu;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int M = w.M;
+  const float target = fminf(1.25f * (float)k + 2.f, 0.5f * (float)(k + CS));
+  const float tiny = tau0 * 1e-6f;
+  const float grow = 1.25f + __fdividef(2.f, (float)k);
+  float tau = tau0;
+
+  for (u32 q = 0; q < w.qn; ++q) {
+    const float4 Q = w.s_pts[w.qoff + q];
+    const u32 qid = w.qs + q;
+    float d[RR];
+#pragma unroll
+    for (int r = 0; r < RR; ++r) {
+      const int slot = lane + 32 * r;
+      const float4 P = w.s_pts[slot];  // slots >= M hold stale but finite data; masked below
+      const float dd = dist2_exact(Q.x, Q.y, Q.z, P.x, P.y, P.z);
+      d[r] = slot < M ? dd : INFINITY;
+    }
+    // ---- threshold search: k <= #{d < tau} <= CS (candidate count ~ linear in tau on a surface) ----
+    int cnt = M;
+    bool ok = true;
+    if (M <= CS) {
+      tau = INFINITY;
+    } else {
+      ok = false;
+      float lo = 0.f, hi = INFINITY, t = tau, flo = 0.f, fhi = (float)M;
+      for (int it = 0; it < 24; ++it) {
+        cnt = 0;
+#pragma unroll
+        for (int r = 0; r < RR; ++r) cnt += __popc(__ballot_sync(FULL, d[r] < t));
+        const float fc = (float)cnt;
+        if (cnt < k) {
+          lo = t;
+          flo = fc;
+        } else if (cnt > CS) {
+          hi = t;
+          fhi = fc;
+        } else {
+          ok = true;
+          break;
+        }
+        float nt;
+        if (hi == INFINITY) {
+          nt = t * fminf(4.f, fmaxf(1.3f, __fdividef(target, fmaxf(fc, 1.f))));
+        } else {
+          nt = lo + (hi - lo) * __fdividef(target - flo, fhi - flo);
+          if (!(nt > lo && nt < hi)) nt = 0.5f * (lo + hi);
+          if (!(nt > lo && nt < hi)) break;  // adjacent floats: a tie cluster larger than CS
+        }
+        t = nt;
+      }
+      tau = t;
+    }
+    bool done = false;
+    if (ok) {
+      // ---- compact the survivors (d2 bits, slot) into shared memory ----
+      int base = 0;
+#pragma unroll
+      for (int r = 0; r < RR; ++r) {
+        const bool p = d[r] < tau;
+        const unsigned m = __ballot_sync(FULL, p);
+        const int pos = base + __popc(m & lt_mask);
+        if (p) {
+          w.s_d2[pos] = __float_as_uint(d[r]);
+          w.s_slot[pos] = (u32)(lane + 32 * r);
+        }
+        base += __popc(m);
+      }
+      __syncwarp();
+      // ---- rank = output slot.  Ranks are counted on d2 alone (non-negative floats order
+      // as unsigned ints); an exact d2 tie makes two ranks collide, which shows as a rank
+      // sum below cnt(cnt-1)/2 and sends the query through the full (d2, index) compare. ----
+      u32 md[E];
+      int rk[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        md[e] = (lane + 32 * e < cnt) ? w.s_d2[lane + 32 * e] : 0xFFFFFFFFu;
+        rk[e] = 0;
+      }
+      {
+        const uint4* v4 = (const uint4*)w.s_d2;
+        const int n4 = cnt >> 2;
+        for (int i = 0; i < n4; ++i) {
+          const uint4 x = v4[i];
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            count_lt(rk[e], x.x, md[e]);
+            count_lt(rk[e], x.y, md[e]);
+            count_lt(rk[e], x.z, md[e]);
+            count_lt(rk[e], x.w, md[e]);
+          }
+        }
+        for (int i = n4 << 2; i < cnt; ++i) {
+          const u32 x = w.s_d2[i];
+#pragma unroll
+          for (int e = 0; e < E; ++e) count_lt(rk[e], x, md[e]);
+        }
+      }
+      int rsum = 0;
+#pragma unroll
+      for (int e = 0; e < E; ++e) rsum += (lane + 32 * e < cnt) ? rk[e] : 0;
+      rsum = __reduce_add_sync(FULL, rsum);
+      if (rsum != (cnt * (cnt - 1)) / 2) {  // exact distance ties: canonical (d2, original index) order
+        u32 mo[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          rk[e] = 0;
+          mo[e] = (lane + 32 * e < cnt) ? __float_as_uint(w.s_pts[w.s_slot[lane + 32 * e]].w) : 0xFFFFFFFFu;
+        }
+        for (int i = 0; i < cnt; ++i) {
+          const u32 x = w.s_d2[i];
+          const u32 xo = __float_as_uint(w.s_pts[w.s_slot[i]].w);
+#pragma unroll
+          for (int e = 0; e < E; ++e) rk[e] += (x < md[e] || (x == md[e] && xo < mo[e])) ? 1 : 0;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        if (lane + 32 * e < cnt && rk[e] < k) {
+          const u32 slot = w.s_slot[lane + 32 * e];
+          nbr[(size_t)qid * k + rk[e]] = w.s_id[slot];
+          nd2[(size_t)qid * k + rk[e]] = __uint_as_float(md[e]);
+          if (rk[e] == k - 1) {
+            kth[qid] = ((u64)md[e] << 32) | (u64)__float_as_uint(w.s_pts[slot].w);
+            *w.s_kd2 = __uint_as_float(md[e]);
+          }
+        }
+      }
+      __syncwarp();
+      const float kd2 = *w.s_kd2;
+      done = kd2 <= qb2[qid];
+      tau = fmaxf(kd2 * grow, tiny);
+      __syncwarp();
+    } else {
+      tau = tau0;
+    }
+    if (!done && lane == 0) fb_list[atomicAdd(fb_count, 1u)] = qid;
+  }
+}
+
 template <int E>  // E = CS / 32 survivor slots per lane
 __global__ void __launch_bounds__(KNN_WARPS * 32)
 knn_cell_kernel(GridView g, const float4* __restrict__ spts, const float* __restrict__ qb2, int k,
@@ -40,20 +204,17 @@ knn_cell_kernel(GridView g, const float4* __restrict__ spts, const float* __rest
                 u32* __restrict__ fb_list, u32* __restrict__ fb_count) {
   constexpr int CS = 32 * E;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4* s_pts_all = (float4*)smem_raw;                                    // [W][CAP]
-  u64* s_key_all = (u64*)(s_pts_all + KNN_WARPS * KNN_CAP);                 // [W][CS]
-  u32* s_id_all = (u32*)(s_key_all + KNN_WARPS * CS);                       // [W][CAP]
-  u32* s_sid_all = s_id_all + KNN_WARPS * KNN_CAP;                          // [W][CS]
-  float* s_kd2_all = (float*)(s_sid_all + KNN_WARPS * CS);                  // [W]
+  float4* s_pts_all = (float4*)smem_raw;                        // [W][CAP] staged candidates
+  u32* s_d2_all = (u32*)(s_pts_all + KNN_WARPS * KNN_CAP);      // [W][CS] survivor d2 bits (16 B aligned)
+  u32* s_id_all = s_d2_all + KNN_WARPS * CS;                    // [W][CAP] sorted ids of the candidates
+  u32* s_slot_all = s_id_all + KNN_WARPS * KNN_CAP;             // [W][CS] survivor slots
+  float* s_kd2_all = (float*)(s_slot_all + KNN_WARPS * CS);     // [W]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const u32 ci = blockIdx.x * KNN_WARPS + warp;
   if (ci >= g.n_cells) return;  // warps are independent: no block-level barrier below
   float4* s_pts = s_pts_all + warp * KNN_CAP;
   u32* s_id = s_id_all + warp * KNN_CAP;
-  u64* s_key = s_key_all + warp * CS;
-  u32* s_sid = s_sid_all + warp * CS;
-  float* s_kd2 = s_kd2_all + warp;
   const unsigned FULL = 0xffffffffu;
 
   // ---- the 27 cells of the block ----
@@ -90,120 +251,39 @@ knn_cell_kernel(GridView g, const float4* __restrict__ spts, const float* __rest
   }
 
   // ---- stage the candidates (coalesced float4 loads) ----
-  for (int j = 0; j < 27; ++j) {
-    u32 cn = __shfl_sync(FULL, ncnt, j);
-    if (cn == 0) continue;
-    u32 s = __shfl_sync(FULL, nstart, j), o = __shfl_sync(FULL, excl, j);
+  unsigned occupied = __ballot_sync(FULL, ncnt != 0);
+  while (occupied) {
+    const int j = __ffs(occupied) - 1;
+    occupied &= occupied - 1;
+    const u32 cn = __shfl_sync(FULL, ncnt, j), s = __shfl_sync(FULL, nstart, j), o = __shfl_sync(FULL, excl, j);
     for (u32 t = lane; t < cn; t += 32) {
       s_pts[o + t] = spts[s + t];
       s_id[o + t] = s + t;
     }
   }
+  // unstaged slots of the last round must hold finite coordinates (they are masked, not skipped)
+  for (int t = M + lane; t < ((M + 31) & ~31); t += 32) s_pts[t] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncwarp();
 
-  const float target = fminf(1.4f * (float)k, 0.5f * (float)(k + CS));
-  const float tiny = tau0 * 1e-6f;
-  float tau = tau0;
-
-  for (u32 q = 0; q < qn; ++q) {
-    const float4 Q = s_pts[qoff + q];
-    const u32 qid = qs + q;
-    float d[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      int slot = lane + 32 * r;
-      if (slot < M) {
-        float4 P = s_pts[slot];
-        d[r] = dist2_exact(Q.x, Q.y, Q.z, P.x, P.y, P.z);
-      } else {
-        d[r] = INFINITY;
-      }
-    }
-    // ---- threshold search: k <= #{d < tau} <= CS ----
-    int cnt = M;
-    bool ok = true;
-    if (M <= CS) {
-      tau = INFINITY;
-    } else {
-      ok = false;
-      float lo = 0.f, hi = INFINITY, t = tau;
-      int clo = 0, chi = M;
-      for (int it = 0; it < 24; ++it) {
-        cnt = 0;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) cnt += __popc(__ballot_sync(FULL, d[r] < t));
-        if (cnt < k) {
-          lo = t;
-          clo = cnt;
-        } else if (cnt > CS) {
-          hi = t;
-          chi = cnt;
-        } else {
-          ok = true;
-          break;
-        }
-        float nt;
-        if (hi == INFINITY) {
-          nt = t * fminf(4.f, fmaxf(1.3f, target / fmaxf((float)cnt, 1.f)));
-        } else {
-          nt = lo + (hi - lo) * ((target - (float)clo) / (float)(chi - clo));
-          if (!(nt > lo && nt < hi)) nt = 0.5f * (lo + hi);
-          if (!(nt > lo && nt < hi)) break;  // adjacent floats: a tie cluster larger than CS
-        }
-        t = nt;
-      }
-      tau = t;
-    }
-    bool done = false;
-    if (ok) {
-      // ---- compact the survivors into shared memory ----
-      int base = 0;
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        bool p = d[r] < tau;
-        unsigned m = __ballot_sync(FULL, p);
-        if (p) {
-          int pos = base + __popc(m & ((1u << lane) - 1u));
-          int slot = lane + 32 * r;
-          s_key[pos] = make_key(d[r], __float_as_uint(s_pts[slot].w));
-          s_sid[pos] = s_id[slot];
-        }
-        base += __popc(m);
-      }
-      __syncwarp();
-      // ---- rank = output slot ----
-      u64 mk[E];
-      int rk[E];
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        mk[e] = (lane + 32 * e < cnt) ? s_key[lane + 32 * e] : KEY_MAX;
-        rk[e] = 0;
-      }
-      for (int i = 0; i < cnt; ++i) {
-        u64 x = s_key[i];
-#pragma unroll
-        for (int e = 0; e < E; ++e) rk[e] += (x < mk[e]) ? 1 : 0;
-      }
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        if (lane + 32 * e < cnt && rk[e] < k) {
-          nbr[(size_t)qid * k + rk[e]] = s_sid[lane + 32 * e];
-          nd2[(size_t)qid * k + rk[e]] = __uint_as_float((u32)(mk[e] >> 32));
-          if (rk[e] == k - 1) {
-            kth[qid] = mk[e];
-            *s_kd2 = __uint_as_float((u32)(mk[e] >> 32));
-          }
-        }
-      }
-      __syncwarp();
-      float kd2 = *s_kd2;
-      done = kd2 <= qb2[qid];
-      tau = fmaxf(kd2 * 1.4f, tiny);
-      __syncwarp();
-    } else {
-      tau = tau0;
-    }
-    if (!done && lane == 0) fb_list[atomicAdd(fb_count, 1u)] = qid;
+  CellWarp w;
+  w.s_pts = s_pts;
+  w.s_id = s_id;
+  w.s_d2 = s_d2_all + warp * CS;
+  w.s_slot = s_slot_all + warp * CS;
+  w.s_kd2 = s_kd2_all + warp;
+  w.M = M;
+  w.qs = qs;
+  w.qn = qn;
+  w.qoff = qoff;
+  switch ((M + 31) >> 5) {
+    case 1: cell_queries<E, 1>(w, qb2, k, tau0, nbr, nd2, kth, fb_list, fb_count, lane); break;
+    case 2: cell_queries<E, 2>(w, qb2, k, tau0, nbr, nd2, kth, fb_list, fb_count, lane); break;
+    case 3: cell_queries<E, 3>(w, qb2, k, tau0, nbr, nd2, kth, fb_list, fb_count, lane); break;
+    case 4: cell_queries<E, 4>(w, qb2, k, tau0, nbr, nd2, kth, fb_list, fb_count, lane); break;
+    case 5: cell_queries<E, 5>(w, qb2, k, tau0, nbr, nd2, kth, fb_list, fb_count, lane); break;
+    case 6: cell_queries<E, 6>(w, qb2, k, tau0, nbr, nd2, kth, fb_list, fb_count, lane); break;
+    case 7: cell_queries<E, 7>(w, qb2, k, tau0, nbr, nd2, kth, fb_list, fb_count, lane); break;
+    default: cell_queries<E, 8>(w, qb2, k, tau0, nbr, nd2, kth, fb_list, fb_count, lane); break;
   }
 }
 
@@ -374,7 +454,7 @@ knn_general_kernel(GridView g, const float4* __restrict__ spts, const float4* __
 // ---------------------------------------------------------------------------
 static size_t cell_kernel_smem(int E) {
   int CS = 32 * E;
-  return (size_t)KNN_WARPS * (KNN_CAP * 16 + CS * 8 + KNN_CAP * 4 + CS * 4) + KNN_WARPS * 4 + 16;
+  return (size_t)KNN_WARPS * (KNN_CAP * 16 + KNN_CAP * 4 + CS * 4 + CS * 4) + KNN_WARPS * 4 + 16;
 }
 
 int knn_run(iftwt_ctx* c, int k) {
@@ -396,15 +476,12 @@ int knn_run(iftwt_ctx* c, int k) {
   const float4* spts = c->spts.as<float4>();
   unsigned blocks = div_up(g.n_cells, KNN_WARPS);
   cudaEventRecord(c->ev0[IFTWT_STAGE_KNN_CELL], c->stream);
-  if (k <= 32) {
-    size_t sm = cell_kernel_smem(2);
-    CU_TRY(c, cudaFuncSetAttribute(knn_cell_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    LAUNCH(c, knn_cell_kernel<2>, blocks, KNN_WARPS * 32, sm, g, spts, c->qb2.as<float>(), k, tau0,
-           c->nbr.as<u32>(), c->nd2.as<float>(), c->kth.as<u64>(), c->fb_list.as<u32>(), fb_count);
-  } else {
-    size_t sm = cell_kernel_smem(4);
-    CU_TRY(c, cudaFuncSetAttribute(knn_cell_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    LAUNCH(c, knn_cell_kernel<4>, blocks, KNN_WARPS * 32, sm, g, spts, c->qb2.as<float>(), k, tau0,
+  {
+    const int E = k <= 16 ? 1 : (k <= 32 ? 2 : 4);
+    auto kern = E == 1 ? knn_cell_kernel<1> : (E == 2 ? knn_cell_kernel<2> : knn_cell_kernel<4>);
+    size_t sm = cell_kernel_smem(E);
+    CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    LAUNCH(c, kern, blocks, KNN_WARPS * 32, sm, g, spts, (const float*)c->qb2.as<float>(), k, tau0,
            c->nbr.as<u32>(), c->nd2.as<float>(), c->kth.as<u64>(), c->fb_list.as<u32>(), fb_count);
   }
   cudaEventRecord(c->ev1[IFTWT_STAGE_KNN_CELL], c->stream);
