@@ -85,6 +85,13 @@ def load_library(build_if_missing: bool = True):
     lib.iftwt_region_seeds.argtypes = [vp, C.POINTER(RgParams), vp, vp, sz, C.POINTER(sz)]
     lib.iftwt_ift.argtypes = [vp, vp, vp, sz, vp, vp]
     lib.iftwt_segment.argtypes = [vp, C.POINTER(SegmentParams), vp, vp, C.POINTER(sz)]
+    lib.iftwt_cloud_resolution.argtypes = [vp, C.c_double, C.POINTER(C.c_double)]
+    lib.iftwt_voxel_graph.argtypes = [vp, C.c_double, C.POINTER(sz)]
+    lib.iftwt_get_cloud.argtypes = [vp, vp, sz, C.POINTER(sz)]
+    lib.iftwt_graph_csr.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
+    lib.iftwt_morph.argtypes = [vp, i32, vp]
+    lib.iftwt_set_intensity.argtypes = [vp, vp]
+    lib.iftwt_regmin_seeds.argtypes = [vp, vp, sz, C.POINTER(sz)]
     lib.iftwt_stage_ms.argtypes = [vp, i32, C.POINTER(f32)]
     lib.iftwt_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.iftwt_reset_counters.argtypes = [vp]
@@ -218,6 +225,52 @@ class Context:
             label = np.empty(self.n, np.uint32) if label is None else label
         self._check(self._lib.iftwt_segment(self._h, C.byref(p), _ptr(cost), _ptr(label), C.byref(ns)))
         return cost, label, ns.value
+
+    # -- graph builder (A), morphology, regional minima ------------------------
+    def cloud_resolution(self, overlap: float = 1.01) -> float:
+        """Graph::computeCloudResolution (graph.hpp:228-259)."""
+        v = C.c_double(0)
+        self._check(self._lib.iftwt_cloud_resolution(self._h, overlap, C.byref(v)))
+        return float(v.value)
+
+    def voxel_graph(self, voxel_size: float) -> int:
+        """Graph::initialize (graph.hpp:293-308); the voxel centres become the cloud."""
+        nv = C.c_size_t(0)
+        self._check(self._lib.iftwt_voxel_graph(self._h, voxel_size, C.byref(nv)))
+        self.n = nv.value
+        return self.n
+
+    def get_cloud(self) -> np.ndarray:
+        out = np.empty((self.n, 4), np.float32)
+        m = C.c_size_t(0)
+        self._check(self._lib.iftwt_get_cloud(self._h, _ptr(out), self.n, C.byref(m)))
+        return out
+
+    def graph_csr(self):
+        narcs = C.c_size_t(0)
+        self._check(self._lib.iftwt_graph_csr(self._h, None, None, 0, C.byref(narcs)))
+        off = np.empty(self.n + 1, np.uint32)
+        adj = np.empty(narcs.value, np.uint32)
+        self._check(self._lib.iftwt_graph_csr(self._h, _ptr(off), _ptr(adj), adj.shape[0], C.byref(narcs)))
+        return off, adj
+
+    def morph(self, op: int) -> np.ndarray:
+        out = np.empty(self.n, np.float32)
+        self._check(self._lib.iftwt_morph(self._h, op, _ptr(out)))
+        return out
+
+    def set_intensity(self, values: np.ndarray):
+        v = np.ascontiguousarray(values, np.float32)
+        assert v.shape[0] == self.n
+        self._check(self._lib.iftwt_set_intensity(self._h, _ptr(v)))
+
+    def regmin_seeds(self) -> np.ndarray:
+        ns = C.c_size_t(0)
+        self._check(self._lib.iftwt_regmin_seeds(self._h, None, 0, C.byref(ns)))
+        seeds = np.empty(ns.value, np.int32)
+        if ns.value:
+            self._check(self._lib.iftwt_regmin_seeds(self._h, _ptr(seeds), ns.value, C.byref(ns)))
+        return seeds
 
     # -- instrumentation -----------------------------------------------------
     def stage_ms(self) -> dict:

@@ -57,6 +57,12 @@ __global__ void export_normals_kernel(const float4* __restrict__ nrm, const u32*
   out[i] = nrm[inv[i]];
 }
 
+
+__global__ void set_intensity_kernel(const float* __restrict__ v, u32 n, float4* __restrict__ pts) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) pts[i].w = v[i];
+}
+
 int check_ctx(iftwt_ctx* c) {
   if (!c) {
     g_err = "null ctx";
@@ -68,6 +74,22 @@ int check_ctx(iftwt_ctx* c) {
 }
 
 }  // namespace
+
+void ctx_invalidate(iftwt_ctx* c) {
+  c->graph_kind = 0;
+  c->grid_valid = false;
+  c->grid_k = 0;
+  c->knn_k = 0;
+  c->graph_k = 0;
+  c->graph_shares_nbr = false;
+  c->mask_k = 0;
+  c->nrm_k = 0;
+  c->seeds_valid = false;
+  c->ift_valid = false;
+  c->n_seeds = 0;
+  c->n_arcs = 0;
+  c->n_rev = 0;
+}
 
 extern "C" {
 
@@ -135,7 +157,7 @@ void iftwt_destroy(iftwt_ctx* c) {
   DevBuf* bufs[] = {&c->pts_in, &c->stage_in, &c->spts, &c->perm, &c->inv, &c->keys, &c->keys_alt, &c->vals_alt,
                     &c->tmp, &c->scalars, &c->cell_key, &c->cell_cnt, &c->cell_start, &c->hkeys, &c->hvals,
                     &c->qb2, &c->nbr, &c->nd2, &c->kth, &c->fb_list, &c->g_off, &c->g_adj, &c->g_deg, &c->g_fwd,
-                    &c->ow_mask, &c->nrm,
+                    &c->ow_mask, &c->nrm, &c->vx_keys, &c->vx_rows, &c->vx_cent, &c->vx_hk, &c->vx_hv,
                     &c->rg_rank, &c->rg_parent, &c->rg_label, &c->rg_aux, &c->rg_aux2, &c->seeds, &c->ift_state,
                     &c->ift_parent, &c->ift_w, &c->ift_byw, &c->ift_local, &c->out_a, &c->out_b};
   for (DevBuf* b : bufs)
@@ -149,20 +171,6 @@ void iftwt_destroy(iftwt_ctx* c) {
   delete c;
 }
 
-static void invalidate(iftwt_ctx* c) {
-  c->grid_valid = false;
-  c->grid_k = 0;
-  c->knn_k = 0;
-  c->graph_k = 0;
-  c->graph_shares_nbr = false;
-  c->mask_k = 0;
-  c->nrm_k = 0;
-  c->seeds_valid = false;
-  c->ift_valid = false;
-  c->n_seeds = 0;
-  c->n_arcs = 0;
-  c->n_rev = 0;
-}
 
 int iftwt_set_cloud(iftwt_ctx* c, const void* points, size_t stride, size_t n, int xyz_off, int i_off) {
   TRY(check_ctx(c));
@@ -170,7 +178,7 @@ int iftwt_set_cloud(iftwt_ctx* c, const void* points, size_t stride, size_t n, i
       (i_off >= 0 && (size_t)i_off + 4 > stride) || (xyz_off & 3) || (i_off >= 0 && (i_off & 3)) || (stride & 3))
     return ctx_fail(c, IFTWT_ERR_INVALID, "bad cloud description (n=%zu stride=%zu xyz_off=%d i_off=%d)", n,
                     stride, xyz_off, i_off);
-  invalidate(c);
+  ctx_invalidate(c);
   ENSURE(c, c->scalars, 4096);
   ENSURE(c, c->pts_in, n * 16);
   StageTimer st(c, IFTWT_STAGE_UPLOAD);
@@ -191,7 +199,7 @@ int iftwt_set_cloud(iftwt_ctx* c, const void* points, size_t stride, size_t n, i
 int iftwt_set_cloud_device(iftwt_ctx* c, const void* device_float4, size_t n) {
   TRY(check_ctx(c));
   if (!device_float4 || n == 0 || n >= 0x7FFFFFF0ull) return ctx_fail(c, IFTWT_ERR_INVALID, "bad device cloud");
-  invalidate(c);
+  ctx_invalidate(c);
   ENSURE(c, c->scalars, 4096);
   ENSURE(c, c->pts_in, n * 16);
   StageTimer st(c, IFTWT_STAGE_UPLOAD);
@@ -373,6 +381,75 @@ int iftwt_segment(iftwt_ctx* c, const iftwt_segment_params* p, uint32_t* cost, u
   }
   CU_TRY(c, cudaStreamSynchronize(c->stream));
   note_fallback(c);
+  return IFTWT_OK;
+}
+
+
+int iftwt_cloud_resolution(iftwt_ctx* c, double overlap, double* voxel_size) {
+  TRY(check_ctx(c));
+  if (!voxel_size) return ctx_fail(c, IFTWT_ERR_INVALID, "null out");
+  if (c->n == 0) return ctx_fail(c, IFTWT_ERR_STATE, "no cloud set");
+  return cloud_resolution_run(c, overlap, voxel_size);
+}
+
+int iftwt_voxel_graph(iftwt_ctx* c, double voxel_size, size_t* n_vertices) {
+  TRY(check_ctx(c));
+  TRY(voxel_graph_run(c, voxel_size, 30));
+  if (n_vertices) *n_vertices = c->n;
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return IFTWT_OK;
+}
+
+int iftwt_get_cloud(iftwt_ctx* c, float* xyzi, size_t cap, size_t* n_points) {
+  TRY(check_ctx(c));
+  if (n_points) *n_points = c->n;
+  if (c->n == 0) return ctx_fail(c, IFTWT_ERR_STATE, "no cloud set");
+  if (xyzi) {
+    if (cap < c->n) return ctx_fail(c, IFTWT_ERR_CAPACITY, "cloud needs %zu points, caller gave %zu", c->n, cap);
+    CU_TRY(c, cudaMemcpyAsync(xyzi, c->pts_in.p, c->n * 16, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+  }
+  return IFTWT_OK;
+}
+
+int iftwt_graph_csr(iftwt_ctx* c, uint32_t* off, uint32_t* adj, size_t cap, size_t* n_arcs) {
+  TRY(check_ctx(c));
+  if (c->graph_k == 0) return ctx_fail(c, IFTWT_ERR_STATE, "graph is not built");
+  return graph_export(c, off, adj, cap, n_arcs);
+}
+
+int iftwt_morph(iftwt_ctx* c, int op, float* out) {
+  TRY(check_ctx(c));
+  if (!out) return ctx_fail(c, IFTWT_ERR_INVALID, "null out");
+  ENSURE(c, c->out_a, c->n * 4);
+  TRY(morph_run(c, op, c->out_a.as<float>()));
+  CU_TRY(c, cudaMemcpyAsync(out, c->out_a.p, c->n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return IFTWT_OK;
+}
+
+int iftwt_set_intensity(iftwt_ctx* c, const float* values) {
+  TRY(check_ctx(c));
+  if (!values || c->n == 0) return ctx_fail(c, IFTWT_ERR_INVALID, "null values or no cloud");
+  ENSURE(c, c->out_b, c->n * 4);
+  CU_TRY(c, cudaMemcpyAsync(c->out_b.p, values, c->n * 4, cudaMemcpyHostToDevice, c->stream));
+  LAUNCH(c, set_intensity_kernel, div_up(c->n, 256), 256, 0, c->out_b.as<float>(), (u32)c->n, c->pts_in.as<float4>());
+  CHECK_LAUNCH(c);
+  c->ift_valid = false;
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return IFTWT_OK;
+}
+
+int iftwt_regmin_seeds(iftwt_ctx* c, int32_t* seeds, size_t cap, size_t* n_seeds) {
+  TRY(check_ctx(c));
+  TRY(regmin_run(c));
+  if (n_seeds) *n_seeds = c->n_seeds;
+  if (seeds) {
+    if (cap < c->n_seeds)
+      return ctx_fail(c, IFTWT_ERR_CAPACITY, "seed buffer needs %zu entries, caller gave %zu", c->n_seeds, cap);
+    if (c->n_seeds) CU_TRY(c, cudaMemcpyAsync(seeds, c->seeds.p, c->n_seeds * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+  }
   return IFTWT_OK;
 }
 

@@ -54,6 +54,7 @@ struct iftwt_ctx {
   void* h_scalars = nullptr;  // pinned mirror
 
   // --- grid ---
+  double bb_lo[3] = {0, 0, 0}, bb_hi[3] = {0, 0, 0};  // float bounding box of the cloud
   bool grid_valid = false;
   int grid_k = 0;
   GridView grid{};
@@ -68,6 +69,7 @@ struct iftwt_ctx {
   DevBuf fb_list;  // u32 [n] fallback query list
   // --- graph ---
   int graph_k = 0;
+  int graph_kind = 0;             // 0 none, 1 symmetric k-NN (builder B), 2 voxel-26 (builder A)
   size_t n_arcs = 0;         // forward (valid, non-self) + reverse arcs
   size_t n_rev = 0;
   bool graph_shares_nbr = false;  // forward rows alias `nbr` (else they live in g_fwd)
@@ -86,6 +88,9 @@ struct iftwt_ctx {
   // --- ift ---
   DevBuf ift_state, ift_parent, ift_w, ift_byw, ift_local;
   bool ift_valid = false;
+  // --- voxel graph (builder A) ---
+  DevBuf vx_keys, vx_rows, vx_cent, vx_hk, vx_hv;
+  double voxel_size = 0.0;
   // --- export scratch ---
   DevBuf out_a, out_b;
 
@@ -139,6 +144,11 @@ int knn_query_run(iftwt_ctx* c, const float4* d_q, size_t m, int k, u32* d_idx_s
 int graph_build(iftwt_ctx* c);                                             // graph.cu
 int knn_mutual_run(iftwt_ctx* c, bool for_graph);
 int graph_detach_rows(iftwt_ctx* c);
+int cloud_resolution_run(iftwt_ctx* c, double overlap, double* res);            // voxel.cu
+int voxel_graph_run(iftwt_ctx* c, double resolution, int k_hint);
+int morph_run(iftwt_ctx* c, int op, float* d_out_orig);
+int regmin_run(iftwt_ctx* c);
+void ctx_invalidate(iftwt_ctx* c);
 int graph_export(iftwt_ctx* c, u32* h_off, u32* h_adj, size_t cap, size_t* n_arcs);
 int normals_run(iftwt_ctx* c);                                             // normals.cu
 int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p);                     // seeds.cu

@@ -106,7 +106,7 @@ int knn_mutual_run(iftwt_ctx* c, bool for_graph) {
 
 int graph_build(iftwt_ctx* c) {
   if (c->knn_k == 0) return ctx_fail(c, IFTWT_ERR_STATE, "k-NN lists are not computed");
-  if (c->graph_k == c->knn_k) return IFTWT_OK;
+  if (c->graph_kind == 1 && c->graph_k == c->knn_k) return IFTWT_OK;
   StageTimer st(c, IFTWT_STAGE_GRAPH);
   const u32 n = (u32)c->n;
   const int k = c->knn_k;
@@ -137,6 +137,7 @@ int graph_build(iftwt_ctx* c) {
   c->n_rev = n_rev;
   c->n_arcs = n_fwd + n_rev;
   c->graph_k = k;
+  c->graph_kind = 1;
   c->graph_shares_nbr = true;
   c->stats.n_arcs = c->n_arcs;
   c->ift_valid = false;

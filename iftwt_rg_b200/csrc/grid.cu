@@ -233,6 +233,10 @@ int grid_build(iftwt_ctx* c, int k) {
     lo[a] = ord2f(hs[a]);
     hi[a] = ord2f(hs[3 + a]);
   }
+  for (int a = 0; a < 3; ++a) {
+    c->bb_lo[a] = lo[a];
+    c->bb_hi[a] = hi[a];
+  }
   double ext = fmax(fmax(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
   if (!(ext > 0.0)) ext = 1.0;
 
@@ -373,6 +377,7 @@ int grid_build(iftwt_ctx* c, int k) {
   // everything derived from an older grid is stale
   c->knn_k = 0;
   c->graph_k = 0;
+  c->graph_kind = 0;
   c->graph_shares_nbr = false;
   c->mask_k = 0;
   c->nrm_k = 0;

@@ -174,6 +174,44 @@ IFTWT_API int iftwt_ift(iftwt_ctx* ctx, const float* weights, const int32_t* see
 IFTWT_API int iftwt_segment(iftwt_ctx* ctx, const iftwt_segment_params* params, uint32_t* cost,
                   uint32_t* label, size_t* n_seeds);
 
+
+/* ---- graph builder (A): the reference's own voxel-26 graph ------------------------- */
+
+/* Graph::computeCloudResolution (graph.hpp:228-259): mean distance to the 2nd nearest
+ * neighbour times `overlap` (1.01 at graph.hpp:34, 5.0 at main.cpp:87).  The mean is the
+ * exact sum of the float terms, rounded once (order independent). */
+IFTWT_API int iftwt_cloud_resolution(iftwt_ctx* ctx, double overlap, double* voxel_size);
+
+/* Graph::initialize (graph.hpp:293-308): occupied voxels of side `voxel_size` (PCL
+ * OctreePointCloudAdjacency), vertices = voxel centres carrying the intensity of their
+ * nearest input point (optimizeGraph, graph.hpp:269-284), edges = occupied 26-neighbours.
+ * As in the reference (graph.hpp:307) the vertices REPLACE the ctx's cloud: every later
+ * call (iftwt_get_cloud, iftwt_normals, iftwt_region_seeds, iftwt_ift ...) works on the
+ * graph's vertices, numbered in ascending Morton order of the octree key. */
+IFTWT_API int iftwt_voxel_graph(iftwt_ctx* ctx, double voxel_size, size_t* n_vertices);
+
+/* Graph::getCloud (graph.hpp:177-180): the current cloud as packed float4 {x,y,z,intensity}. */
+IFTWT_API int iftwt_get_cloud(iftwt_ctx* ctx, float* xyzi, size_t capacity_points, size_t* n_points);
+
+/* Graph::getAdjacencyList (graph.hpp:63-66) for whichever graph is current, as CSR in
+ * original vertex ids, rows ascending, no self loops. */
+IFTWT_API int iftwt_graph_csr(iftwt_ctx* ctx, uint32_t* off, uint32_t* adj, size_t adj_capacity, size_t* n_arcs);
+
+/* Graph::morph_* (graph.hpp:131-163, 323-371) over the closed neighbourhood.
+ * op: 1 bin_erode, 2 bin_dilate, 3 dilate, 4 erode (enum MORPH, graph.hpp:13), 5 gradient. */
+enum { IFTWT_MORPH_BIN_ERODE = 1, IFTWT_MORPH_BIN_DILATE = 2, IFTWT_MORPH_DILATE = 3, IFTWT_MORPH_ERODE = 4,
+       IFTWT_MORPH_GRADIENT = 5 };
+IFTWT_API int iftwt_morph(iftwt_ctx* ctx, int op, float* out);
+
+/* Graph::pc_to_g / morph_erode_gradient write-back (graph.hpp:164-176, 203-208): replace the
+ * vertex intensities (n floats, original order). */
+IFTWT_API int iftwt_set_intensity(iftwt_ctx* ctx, const float* values);
+
+/* Graph::getRegmin (graph.hpp:209-226), the seeds of IFT_PCD(Graph&) (ift.hpp:38-44):
+ * vertices whose value is 0 or the minimum of their closed neighbourhood.  Leaves them on
+ * the device for iftwt_ift(seeds = NULL). */
+IFTWT_API int iftwt_regmin_seeds(iftwt_ctx* ctx, int32_t* seeds, size_t capacity, size_t* n_seeds);
+
 /* Instrumentation (the reference's is one std::time pair, ift.hpp:172-173). */
 IFTWT_API int iftwt_stage_ms(iftwt_ctx* ctx, int stage, float* ms); /* CUDA-event time of the last run of a stage */
 IFTWT_API int iftwt_get_stats(iftwt_ctx* ctx, iftwt_stats* out);

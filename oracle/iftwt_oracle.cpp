@@ -26,6 +26,7 @@
 //     with  -ffp-contract=off  (no FMA contraction), see oracle/Makefile.
 // =============================================================================
 #include <algorithm>
+#include <array>
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
@@ -925,4 +926,161 @@ ORC_API double orc_cloud_resolution(const float* pts4, i64 n, double overlap, in
   }
   if (cnt != 0) res *= overlap;  // graph.hpp:256
   return res;
+}
+
+// -----------------------------------------------------------------------------
+// pcl::octree::OctreePointCloudAdjacency as driven by Graph::initialize
+// (graph.hpp:293-308) [PCL-recall App. A.2]: bounding box over the points,
+// getKeyBitSize (depth, symmetric padding to side 2^depth * res, binary64), key =
+// (unsigned)((p - min') / res) per axis, vertex = voxel CENTRE, neighbours = occupied
+// voxels at key offsets {-1,0,1}^3 clipped to [0, max_key].  Vertices are numbered in
+// ascending Morton order of the key (x = most significant axis bit): the canonical
+// stand-in for the reference's address order.  The self loop PCL adds is NOT emitted
+// in the CSR (morphology / regmin add the vertex itself explicitly).
+// Graph::optimizeGraph (graph.hpp:269-284): vertex intensity = intensity of the
+// nearest original point.
+// Outputs: centres4[V] {x,y,z,intensity}, keys3[V*3], off[V+1], adj (cap 26 V),
+// box[4] = {min_x', min_y', min_z', depth}.  Returns V.
+// -----------------------------------------------------------------------------
+static inline u64 morton_spread21(u64 v) {
+  u64 x = v & 0x1FFFFFull;
+  x = (x | x << 32) & 0x1F00000000FFFFull;
+  x = (x | x << 16) & 0x1F0000FF0000FFull;
+  x = (x | x << 8) & 0x100F00F00F00F00Full;
+  x = (x | x << 4) & 0x10C30C30C30C30C3ull;
+  x = (x | x << 2) & 0x1249249249249249ull;
+  return x;
+}
+static inline u64 morton_xyz(u32 x, u32 y, u32 z) {
+  return (morton_spread21(x) << 2) | (morton_spread21(y) << 1) | morton_spread21(z);
+}
+
+ORC_API i64 orc_voxel_graph(const float* pts4, i64 n, double resolution, float* centres4, u32* keys3,
+                            u32* off, u32* adj, double* box) {
+  double mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (i64 i = 0; i < n; ++i) {
+    const float* p = pts4 + 4 * i;
+    if (!std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2])) continue;
+    for (int a = 0; a < 3; ++a) {
+      if (p[a] < mn[a]) mn[a] = p[a];
+      if (p[a] > mx[a]) mx[a] = p[a];
+    }
+  }
+  // OctreePointCloud::getKeyBitSize
+  const float minValue = FLT_EPSILON;
+  unsigned mk[3];
+  for (int a = 0; a < 3; ++a) mk[a] = (unsigned)std::ceil((mx[a] - mn[a] - minValue) / resolution);
+  unsigned max_voxels = std::max(std::max(std::max(mk[0], mk[1]), mk[2]), 2u);
+  unsigned depth = std::max(std::min(32u, (unsigned)std::ceil(std::log((double)max_voxels) / std::log(2.0) - minValue)), 0u);
+  double side = (double)(1u << depth) * resolution;
+  for (int a = 0; a < 3; ++a) {
+    double over = (side - (mx[a] - mn[a])) / 2.0;
+    if (over > minValue) {
+      mn[a] -= over;
+      mx[a] += over;
+    }
+  }
+  const u32 max_key = (1u << depth) - 1u;
+  if (box) {
+    box[0] = mn[0]; box[1] = mn[1]; box[2] = mn[2]; box[3] = (double)depth;
+  }
+  // keys
+  std::vector<std::pair<u64, std::array<u32, 3>>> vox;
+  vox.reserve((size_t)n);
+  for (i64 i = 0; i < n; ++i) {
+    const float* p = pts4 + 4 * i;
+    if (!std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2])) continue;
+    std::array<u32, 3> k;
+    for (int a = 0; a < 3; ++a) k[a] = (u32)(((double)p[a] - mn[a]) / resolution);
+    vox.push_back({morton_xyz(k[0], k[1], k[2]), k});
+  }
+  std::sort(vox.begin(), vox.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+  vox.erase(std::unique(vox.begin(), vox.end(), [](const auto& a, const auto& b) { return a.first == b.first; }),
+            vox.end());
+  const i64 V = (i64)vox.size();
+  std::vector<float> q((size_t)V * 4);
+  for (i64 v = 0; v < V; ++v) {
+    for (int a = 0; a < 3; ++a) {
+      keys3[3 * v + a] = vox[v].second[a];
+      q[4 * v + a] = (float)(((double)vox[v].second[a] + 0.5f) * resolution + mn[a]);
+    }
+    q[4 * v + 3] = 0.f;
+  }
+  // optimizeGraph: intensity of the nearest original point
+  std::vector<int32_t> nn((size_t)V);
+  knn_run(pts4, n, q.data(), V, 1, nn.data(), nullptr);
+  for (i64 v = 0; v < V; ++v) {
+    for (int a = 0; a < 3; ++a) centres4[4 * v + a] = q[4 * v + a];
+    centres4[4 * v + 3] = nn[v] >= 0 ? pts4[4 * (i64)nn[v] + 3] : 0.f;
+  }
+  // computeNeighbors
+  i64 tot = 0;
+  for (i64 v = 0; v < V; ++v) {
+    off[v] = (u32)tot;
+    const auto& k = vox[v].second;
+    std::vector<u32> row;
+    for (int dx = (k[0] > 0 ? -1 : 0); dx <= (k[0] == max_key ? 0 : 1); ++dx)
+      for (int dy = (k[1] > 0 ? -1 : 0); dy <= (k[1] == max_key ? 0 : 1); ++dy)
+        for (int dz = (k[2] > 0 ? -1 : 0); dz <= (k[2] == max_key ? 0 : 1); ++dz) {
+          if (dx == 0 && dy == 0 && dz == 0) continue;
+          u64 code = morton_xyz(k[0] + dx, k[1] + dy, k[2] + dz);
+          auto it = std::lower_bound(vox.begin(), vox.end(), code,
+                                     [](const auto& a, u64 c) { return a.first < c; });
+          if (it != vox.end() && it->first == code) row.push_back((u32)(it - vox.begin()));
+        }
+    std::sort(row.begin(), row.end());
+    for (u32 r : row) adj[tot++] = r;
+  }
+  off[V] = (u32)tot;
+  return V;
+}
+
+// Graph::morph_base (graph.hpp:323-371) over the CLOSED neighbourhood (PCL's voxel
+// adjacency carries a self loop, App. A.2).  op: 1 bin_erode, 2 bin_dilate, 3 dilate,
+// 4 erode (enum MORPH, graph.hpp:13), 5 gradient = dilate - erode (graph.hpp:147-163).
+// bin_dilate: the reference discards its result (shadowed local, graph.hpp:345-349) and
+// always writes 0; this restatement implements the evident intent (App. B #3).
+ORC_API void orc_morph(const u32* off, const u32* adj, i64 n, const float* inten, int op, float* out) {
+  auto one = [&](i64 v, int o) -> float {
+    float r;
+    if (o == 4) {
+      r = 255.f;
+      if (inten[v] < r) r = inten[v];
+      for (u32 e = off[v]; e < off[v + 1]; ++e)
+        if (inten[adj[e]] < r) r = inten[adj[e]];
+    } else if (o == 3) {
+      r = 0.f;
+      if (inten[v] > r) r = inten[v];
+      for (u32 e = off[v]; e < off[v + 1]; ++e)
+        if (inten[adj[e]] > r) r = inten[adj[e]];
+    } else if (o == 1) {
+      bool hit = inten[v] == 0.f;
+      for (u32 e = off[v]; e < off[v + 1]; ++e) hit = hit || inten[adj[e]] == 0.f;
+      r = hit ? 0.f : 255.f;
+    } else {
+      bool hit = inten[v] == 255.f;
+      for (u32 e = off[v]; e < off[v + 1]; ++e) hit = hit || inten[adj[e]] == 255.f;
+      r = hit ? 255.f : 0.f;
+    }
+    return r;
+  };
+#pragma omp parallel for schedule(static)
+  for (i64 v = 0; v < n; ++v) out[v] = op == 5 ? one(v, 3) - one(v, 4) : one(v, op);
+}
+
+// Graph::getRegmin (graph.hpp:209-226): a vertex is a seed if its value is 0 or equals
+// the minimum over its closed neighbourhood.  Returns the count; seeds ascending.
+ORC_API i64 orc_regmin(const u32* off, const u32* adj, i64 n, const float* inten, int32_t* seeds) {
+  i64 m = 0;
+  for (i64 v = 0; v < n; ++v) {
+    float val = inten[v];
+    bool is_min = val == 0.f;
+    if (!is_min) {
+      float mn = val;
+      for (u32 e = off[v]; e < off[v + 1]; ++e) mn = std::min(mn, inten[adj[e]]);
+      is_min = val == mn;
+    }
+    if (is_min) seeds[m++] = (int32_t)v;
+  }
+  return m;
 }

@@ -177,3 +177,39 @@ def cloud_resolution(pts, overlap=1.01, mode=0) -> float:
     pts = _pts(pts)
     return float(lib().orc_cloud_resolution(_p(pts), C.c_int64(pts.shape[0]), C.c_double(overlap),
                                             C.c_int(mode)))
+
+
+def voxel_graph(pts, resolution):
+    pts = _pts(pts)
+    n = pts.shape[0]
+    cen = np.empty((n, 4), np.float32)
+    keys = np.empty((n, 3), np.uint32)
+    off = np.empty(n + 1, np.uint32)
+    adj = np.empty(26 * n, np.uint32)
+    box = np.empty(4, np.float64)
+    lib().orc_voxel_graph.restype = C.c_int64
+    V = int(lib().orc_voxel_graph(_p(pts), C.c_int64(n), C.c_double(resolution), _p(cen), _p(keys), _p(off),
+                                  _p(adj), _p(box)))
+    return cen[:V].copy(), keys[:V].copy(), off[:V + 1].copy(), adj[:off[V]].copy(), box
+
+
+MORPH_BIN_ERODE, MORPH_BIN_DILATE, MORPH_DILATE, MORPH_ERODE, MORPH_GRADIENT = 1, 2, 3, 4, 5
+
+
+def morph(off, adj, inten, op):
+    off = np.ascontiguousarray(off, np.uint32)
+    adj = np.ascontiguousarray(adj, np.uint32)
+    inten = np.ascontiguousarray(inten, np.float32)
+    out = np.empty_like(inten)
+    lib().orc_morph(_p(off), _p(adj), C.c_int64(len(inten)), _p(inten), C.c_int(op), _p(out))
+    return out
+
+
+def regmin(off, adj, inten):
+    off = np.ascontiguousarray(off, np.uint32)
+    adj = np.ascontiguousarray(adj, np.uint32)
+    inten = np.ascontiguousarray(inten, np.float32)
+    seeds = np.empty(len(inten), np.int32)
+    lib().orc_regmin.restype = C.c_int64
+    m = int(lib().orc_regmin(_p(off), _p(adj), C.c_int64(len(inten)), _p(inten), _p(seeds)))
+    return seeds[:m].copy()
