@@ -92,6 +92,9 @@ def load_library(build_if_missing: bool = True):
     lib.iftwt_morph.argtypes = [vp, i32, vp]
     lib.iftwt_set_intensity.argtypes = [vp, vp]
     lib.iftwt_regmin_seeds.argtypes = [vp, vp, sz, C.POINTER(sz)]
+    lib.iftwt_region_adjacency.argtypes = [vp, vp, vp, vp, sz, C.POINTER(sz)]
+    lib.iftwt_region_info.argtypes = [vp, vp, vp, vp, sz, C.POINTER(sz)]
+    lib.iftwt_cluster.argtypes = [vp, i32, vp, C.POINTER(sz)]
     lib.iftwt_stage_ms.argtypes = [vp, i32, C.POINTER(f32)]
     lib.iftwt_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.iftwt_reset_counters.argtypes = [vp]
@@ -271,6 +274,35 @@ class Context:
         if ns.value:
             self._check(self._lib.iftwt_regmin_seeds(self._h, _ptr(seeds), ns.value, C.byref(ns)))
         return seeds
+
+    # -- region hierarchy ------------------------------------------------------
+    def region_adjacency(self):
+        m = C.c_size_t(0)
+        self._check(self._lib.iftwt_region_adjacency(self._h, None, None, None, 0, C.byref(m)))
+        a = np.empty(m.value, np.uint32)
+        b = np.empty(m.value, np.uint32)
+        s = np.empty(m.value, np.uint32)
+        if m.value:
+            self._check(self._lib.iftwt_region_adjacency(self._h, _ptr(a), _ptr(b), _ptr(s), m.value, C.byref(m)))
+        return a, b, s
+
+    def region_info(self):
+        m = C.c_size_t(0)
+        self._check(self._lib.iftwt_region_info(self._h, None, None, None, 0, C.byref(m)))
+        seed = np.empty(m.value, np.uint32)
+        area = np.empty(m.value, np.uint32)
+        height = np.empty(m.value, np.float32)
+        if m.value:
+            self._check(self._lib.iftwt_region_info(self._h, _ptr(seed), _ptr(area), _ptr(height), m.value,
+                                                    C.byref(m)))
+        return seed, area, height
+
+    def cluster(self, num_regions: int = 10):
+        """Cluster(..., num_regions) + getLabelCloud (cluster.hpp:25-81; main.cpp:124-126)."""
+        out = np.empty(self.n, np.uint32)
+        k = C.c_size_t(0)
+        self._check(self._lib.iftwt_cluster(self._h, num_regions, _ptr(out), C.byref(k)))
+        return out, k.value
 
     # -- instrumentation -----------------------------------------------------
     def stage_ms(self) -> dict:

@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <new>
+#include <vector>
 
 #include "common.cuh"
 
@@ -89,6 +90,7 @@ void ctx_invalidate(iftwt_ctx* c) {
   c->n_seeds = 0;
   c->n_arcs = 0;
   c->n_rev = 0;
+  c->rag_valid = false;
 }
 
 extern "C" {
@@ -157,7 +159,7 @@ void iftwt_destroy(iftwt_ctx* c) {
   DevBuf* bufs[] = {&c->pts_in, &c->stage_in, &c->spts, &c->perm, &c->inv, &c->keys, &c->keys_alt, &c->vals_alt,
                     &c->tmp, &c->scalars, &c->cell_key, &c->cell_cnt, &c->cell_start, &c->hkeys, &c->hvals,
                     &c->qb2, &c->nbr, &c->nd2, &c->kth, &c->fb_list, &c->g_off, &c->g_adj, &c->g_deg, &c->g_fwd,
-                    &c->ow_mask, &c->nrm, &c->vx_keys, &c->vx_rows, &c->vx_cent, &c->vx_hk, &c->vx_hv,
+                    &c->ow_mask, &c->nrm, &c->vx_keys, &c->vx_rows, &c->vx_cent, &c->vx_hk, &c->vx_hv, &c->ift_res, &c->ift_wf, &c->h_keys, &c->h_vals, &c->h_pairs, &c->h_seeds, &c->h_info,
                     &c->rg_rank, &c->rg_parent, &c->rg_label, &c->rg_aux, &c->rg_aux2, &c->seeds, &c->ift_state,
                     &c->ift_parent, &c->ift_w, &c->ift_byw, &c->ift_local, &c->out_a, &c->out_b};
   for (DevBuf* b : bufs)
@@ -450,6 +452,59 @@ int iftwt_regmin_seeds(iftwt_ctx* c, int32_t* seeds, size_t cap, size_t* n_seeds
     if (c->n_seeds) CU_TRY(c, cudaMemcpyAsync(seeds, c->seeds.p, c->n_seeds * 4, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
   }
+  return IFTWT_OK;
+}
+
+int iftwt_region_adjacency(iftwt_ctx* c, uint32_t* a, uint32_t* b, uint32_t* saddle, size_t cap, size_t* n_pairs) {
+  TRY(check_ctx(c));
+  TRY(region_adjacency_run(c));
+  const size_t m = c->n_pairs;
+  if (n_pairs) *n_pairs = m;
+  if (a || b || saddle) {
+    if (cap < m) return ctx_fail(c, IFTWT_ERR_CAPACITY, "pair buffers need %zu entries, caller gave %zu", m, cap);
+    if (m) {
+      std::vector<u64> keys(m);
+      CU_TRY(c, cudaMemcpyAsync(keys.data(), c->h_pairs.p, m * 8, cudaMemcpyDeviceToHost, c->stream));
+      if (saddle)
+        CU_TRY(c, cudaMemcpyAsync(saddle, (char*)c->h_pairs.p + c->pairs_vals_offset, m * 4, cudaMemcpyDeviceToHost,
+                                  c->stream));
+      CU_TRY(c, cudaStreamSynchronize(c->stream));
+      for (size_t i = 0; i < m; ++i) {
+        if (a) a[i] = (uint32_t)(keys[i] >> 32);
+        if (b) b[i] = (uint32_t)keys[i];
+      }
+    }
+  }
+  return IFTWT_OK;
+}
+
+int iftwt_region_info(iftwt_ctx* c, uint32_t* seed, uint32_t* area, float* height, size_t cap, size_t* n_regions) {
+  TRY(check_ctx(c));
+  TRY(region_info_run(c));
+  const size_t nr = c->n_regions;
+  if (n_regions) *n_regions = nr;
+  if (seed || area || height) {
+    if (cap < nr) return ctx_fail(c, IFTWT_ERR_CAPACITY, "region buffers need %zu entries, caller gave %zu", nr, cap);
+    if (nr) {
+      if (seed)
+        CU_TRY(c, cudaMemcpyAsync(seed, c->h_seeds.as<u32>() + (c->n_seeds + 1), nr * 4, cudaMemcpyDeviceToHost,
+                                  c->stream));
+      if (area) CU_TRY(c, cudaMemcpyAsync(area, c->h_info.p, nr * 4, cudaMemcpyDeviceToHost, c->stream));
+      if (height)
+        CU_TRY(c, cudaMemcpyAsync(height, c->h_info.as<u32>() + (nr + 1), nr * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+  }
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return IFTWT_OK;
+}
+
+int iftwt_cluster(iftwt_ctx* c, int num_regions, uint32_t* cluster_of, size_t* n_clusters) {
+  TRY(check_ctx(c));
+  if (!c->ift_valid) return ctx_fail(c, IFTWT_ERR_STATE, "no IFT result on the device");
+  ENSURE(c, c->out_b, c->n * 4);
+  TRY(cluster_run(c, num_regions, c->out_b.as<u32>(), n_clusters));
+  if (cluster_of) CU_TRY(c, cudaMemcpyAsync(cluster_of, c->out_b.p, c->n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
   return IFTWT_OK;
 }
 

@@ -87,6 +87,12 @@ struct iftwt_ctx {
   bool seeds_valid = false;
   // --- ift ---
   DevBuf ift_state, ift_parent, ift_w, ift_byw, ift_local;
+  DevBuf ift_res;  // u64 [n] resolved (cost << 32 | label) per sorted vertex
+  DevBuf ift_wf;   // float [n] the weights the IFT ran on, sorted space
+  // --- hierarchy ---
+  DevBuf h_keys, h_vals, h_pairs, h_seeds, h_info;
+  size_t n_pairs = 0, n_regions = 0, pairs_vals_offset = 0;
+  bool rag_valid = false;
   bool ift_valid = false;
   // --- voxel graph (builder A) ---
   DevBuf vx_keys, vx_rows, vx_cent, vx_hk, vx_hv;
@@ -148,6 +154,9 @@ int cloud_resolution_run(iftwt_ctx* c, double overlap, double* res);            
 int voxel_graph_run(iftwt_ctx* c, double resolution, int k_hint);
 int morph_run(iftwt_ctx* c, int op, float* d_out_orig);
 int regmin_run(iftwt_ctx* c);
+int region_adjacency_run(iftwt_ctx* c);                                     // hierarchy.cu
+int region_info_run(iftwt_ctx* c);
+int cluster_run(iftwt_ctx* c, int num_regions, u32* d_cluster_orig, size_t* n_clusters);
 void ctx_invalidate(iftwt_ctx* c);
 int graph_export(iftwt_ctx* c, u32* h_off, u32* h_adj, size_t cap, size_t* n_arcs);
 int normals_run(iftwt_ctx* c);                                             // normals.cu

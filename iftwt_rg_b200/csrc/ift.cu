@@ -64,11 +64,12 @@ __device__ __forceinline__ void uf_union_roots(u32* parent, u32 ra, u32 rb) {
 __global__ void ift_init_kernel(const float* __restrict__ w_orig, const float4* __restrict__ pts_in,
                                 const u32* __restrict__ perm, u32 n, unsigned short* __restrict__ w16,
                                 u64* __restrict__ state, u32* __restrict__ parent, u32* __restrict__ ids,
-                                u32* __restrict__ bad) {
+                                float* __restrict__ wf, u32* __restrict__ bad) {
   u32 v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n) return;
   u32 o = perm[v];
   float w = w_orig ? w_orig[o] : pts_in[o].w;
+  wf[v] = w;
   unsigned short q;
   if (!(w >= 0.f) || w != floorf(w)) {
     atomicAdd(bad, 1u);
@@ -164,20 +165,18 @@ __global__ void ift_level_settle_kernel(const u32* __restrict__ byw, u32 seg_beg
 }
 // every vertex reads its component's word; unconquered vertices keep (500, self)
 __global__ void ift_resolve_kernel(u32* __restrict__ parent, u64* __restrict__ state, const u32* __restrict__ perm,
-                                   u32 n, u32* __restrict__ cost_o, u32* __restrict__ label_o) {
+                                   u32 n, u32* __restrict__ cost_o, u32* __restrict__ label_o,
+                                   u64* __restrict__ res) {
   u32 v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n) return;
   u32 r = uf_find(parent, v);
   u64 s = state[r];
   u32 o = perm[v];
   u32 cst = (u32)(s >> 32);
-  if (cst < IFTWT_MAX_COST) {
-    cost_o[o] = cst;
-    label_o[o] = (u32)s;
-  } else {
-    cost_o[o] = IFTWT_MAX_COST;
-    label_o[o] = o;
-  }
+  if (cst >= IFTWT_MAX_COST) s = ((u64)IFTWT_MAX_COST << 32) | (u64)o;
+  cost_o[o] = (u32)(s >> 32);
+  label_o[o] = (u32)s;
+  res[v] = s;
 }
 
 }  // namespace
@@ -191,6 +190,8 @@ int ift_run(iftwt_ctx* c, const float* d_w_orig, const u32* d_seeds_orig, size_t
   ENSURE(c, c->ift_w, (size_t)n * 2 * 2 + 16);
   ENSURE(c, c->ift_byw, (size_t)n * 4 * 2);
   ENSURE(c, c->ift_local, (size_t)n * 4);
+  ENSURE(c, c->ift_res, (size_t)n * 8);
+  ENSURE(c, c->ift_wf, (size_t)n * 4);
   ENSURE(c, c->out_a, (size_t)n * 4 * 2);
   u64* state = c->ift_state.as<u64>();
   u32* parent = c->ift_parent.as<u32>();
@@ -205,7 +206,7 @@ int ift_run(iftwt_ctx* c, const float* d_w_orig, const u32* d_seeds_orig, size_t
   u32* d_seg = sc + 128;  // 513 entries
   CU_TRY(c, cudaMemsetAsync(d_bad, 0, 8, c->stream));
   LAUNCH(c, ift_init_kernel, div_up(n, 256), 256, 0, d_w_orig, c->pts_in.as<float4>(), c->perm.as<u32>(), n, w16,
-         state, parent, ids, d_bad);
+         state, parent, ids, c->ift_wf.as<float>(), d_bad);
   if (ns) LAUNCH(c, ift_seed_kernel, div_up(ns, 256), 256, 0, d_seeds_orig, (u32)ns, c->inv.as<u32>(), n, w16,
                  state, d_bad);
   CHECK_LAUNCH(c);
@@ -238,9 +239,11 @@ int ift_run(iftwt_ctx* c, const float* d_w_orig, const u32* d_seeds_orig, size_t
   CHECK_LAUNCH(c);
   u32* cost_o = c->out_a.as<u32>();
   u32* label_o = cost_o + n;
-  LAUNCH(c, ift_resolve_kernel, div_up(n, 256), 256, 0, parent, state, c->perm.as<u32>(), n, cost_o, label_o);
+  LAUNCH(c, ift_resolve_kernel, div_up(n, 256), 256, 0, parent, state, c->perm.as<u32>(), n, cost_o, label_o,
+         c->ift_res.as<u64>());
   CHECK_LAUNCH(c);
   c->stats.ift_levels = levels;
   c->ift_valid = true;
+  c->rag_valid = false;
   return IFTWT_OK;
 }

@@ -411,6 +411,7 @@ int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p) {
     CHECK_LAUNCH(c);
   }
   c->seeds_valid = true;
+  c->ift_valid = false;
   c->stats.n_seeds = n_kept;
   return IFTWT_OK;
 }

@@ -361,6 +361,7 @@ int regmin_run(iftwt_ctx* c) {
   CU_TRY(c, cudaStreamSynchronize(c->stream));
   c->n_seeds = hs[125];
   c->seeds_valid = true;
+  c->ift_valid = false;
   c->stats.n_seeds = c->n_seeds;
   return IFTWT_OK;
 }

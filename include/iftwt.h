@@ -212,6 +212,25 @@ IFTWT_API int iftwt_set_intensity(iftwt_ctx* ctx, const float* values);
  * the device for iftwt_ift(seeds = NULL). */
 IFTWT_API int iftwt_regmin_seeds(iftwt_ctx* ctx, int32_t* seeds, size_t capacity, size_t* n_seeds);
 
+/* ---- region hierarchy (ift.hpp:5-23, 207-243; cluster.hpp:23-229) ---------------------
+ * The reference's region bookkeeping and Cluster depend on the sequential conquest order
+ * and on container address order; the product definition is the
+ * watershed region-adjacency graph with saddle heights and a single-linkage merge along
+ * its minimum spanning forest.  All three calls need a finished iftwt_ift / iftwt_segment. */
+
+/* Region adjacency: pairs a < b of seed ids whose regions touch, saddle = min over the
+ * touching arcs of max(cost[u], cost[v]).  Sorted by (a, b).  Replaces getMST (ift.hpp:45-47). */
+IFTWT_API int iftwt_region_adjacency(iftwt_ctx* ctx, uint32_t* a, uint32_t* b, uint32_t* saddle, size_t capacity,
+                           size_t* n_pairs);
+/* Region attributes, sorted by seed id: area = conquered vertices, height = max vertex
+ * value (the order-free part of r_info, ift.hpp:5-23). */
+IFTWT_API int iftwt_region_info(iftwt_ctx* ctx, uint32_t* seed, uint32_t* area, float* height, size_t capacity,
+                      size_t* n_regions);
+/* Cluster(mst, root_m, g_v, num_regions) + getLabelCloud (cluster.hpp:25-81): merge the
+ * regions down to num_regions; cluster_of[n] = smallest seed id of the vertex's cluster,
+ * 0xFFFFFFFF for vertices the IFT never conquered. */
+IFTWT_API int iftwt_cluster(iftwt_ctx* ctx, int num_regions, uint32_t* cluster_of, size_t* n_clusters);
+
 /* Instrumentation (the reference's is one std::time pair, ift.hpp:172-173). */
 IFTWT_API int iftwt_stage_ms(iftwt_ctx* ctx, int stage, float* ms); /* CUDA-event time of the last run of a stage */
 IFTWT_API int iftwt_get_stats(iftwt_ctx* ctx, iftwt_stats* out);

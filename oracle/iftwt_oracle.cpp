@@ -33,6 +33,7 @@
 #include <cstdio>
 #include <cstring>
 #include <deque>
+#include <functional>
 #include <map>
 #include <numeric>
 #include <queue>
@@ -1083,4 +1084,225 @@ ORC_API i64 orc_regmin(const u32* off, const u32* adj, i64 n, const float* inten
     if (is_min) seeds[m++] = (int32_t)v;
   }
   return m;
+}
+
+// =============================================================================
+// Region hierarchy (I4 / L1)
+// =============================================================================
+// The reference interleaves region attributes and a first-contact "MST" with the
+// heap loop (ift.hpp:207-243) and merges regions in Cluster (cluster.hpp:83-221).
+// Both depend on the sequential conquest order and on container address order, so they
+// have no order-free equivalent (hard part 7).  Two restatements follow:
+//   * the PRODUCT DEFINITION (what the GPU path implements, bit-exact contract):
+//     region adjacency with watershed saddles, area/height attributes, single-linkage
+//     merge of the regions down to num_regions along the saddle minimum spanning forest;
+//   * the LITERAL Cluster of cluster.hpp on the literal MST of ift.hpp (informational).
+
+// Region adjacency: for every pair of adjacent conquered vertices with different labels,
+// saddle(a,b) = min over such arcs of max(cost[u], cost[v]).  Output rows sorted by
+// (a, b), a < b.  Returns the number of pairs (call with cap = 0 to count).
+ORC_API i64 orc_region_adjacency(const u32* off, const u32* adj, i64 n, const u32* cost, const u32* label,
+                                 u32* ra, u32* rb, u32* saddle, i64 cap) {
+  std::map<std::pair<u32, u32>, u32> tab;
+  for (i64 u = 0; u < n; ++u) {
+    if (cost[u] >= MAX_COST) continue;
+    for (u32 e = off[u]; e < off[u + 1]; ++e) {
+      u32 v = adj[e];
+      if (cost[v] >= MAX_COST || label[v] == label[u]) continue;
+      u32 a = std::min(label[u], label[v]), b = std::max(label[u], label[v]);
+      u32 s = std::max(cost[u], cost[v]);
+      auto it = tab.find({a, b});
+      if (it == tab.end()) tab[{a, b}] = s;
+      else if (s < it->second) it->second = s;
+    }
+  }
+  i64 m = 0;
+  for (auto& kv : tab) {
+    if (m < cap) {
+      ra[m] = kv.first.first;
+      rb[m] = kv.first.second;
+      saddle[m] = kv.second;
+    }
+    ++m;
+  }
+  return m;
+}
+
+// Region attributes in the spirit of r_info (ift.hpp:5-23), order-free part only:
+// area = number of conquered vertices (seed included), height = max vertex value over
+// them (the seed's own value included, ift.hpp:140-141).  Regions sorted by seed id.
+ORC_API i64 orc_region_info(i64 n, const float* w, const u32* cost, const u32* label, u32* seed, u32* area,
+                            float* height, i64 cap) {
+  std::map<u32, std::pair<u32, float>> tab;
+  for (i64 v = 0; v < n; ++v) {
+    if (cost[v] >= MAX_COST) continue;
+    auto& e = tab[label[v]];
+    e.first += 1;
+    e.second = std::max(e.second, w[v]);
+  }
+  i64 m = 0;
+  for (auto& kv : tab) {
+    if (m < cap) {
+      seed[m] = kv.first;
+      area[m] = kv.second.first;
+      height[m] = kv.second.second;
+    }
+    ++m;
+  }
+  return m;
+}
+
+// Single-linkage merge along the saddle minimum spanning forest: Kruskal over the pairs
+// in ascending (saddle, a, b), stopping when num_regions clusters remain (or no pair is
+// left).  cluster_of[v] = smallest seed id of v's merged cluster, or 0xFFFFFFFF for
+// unconquered vertices.  Returns the number of clusters.
+ORC_API i64 orc_cluster_saddle(i64 n, const u32* cost, const u32* label, const u32* ra, const u32* rb,
+                               const u32* saddle, i64 m, int num_regions, u32* cluster_of) {
+  std::vector<u32> seeds;
+  for (i64 v = 0; v < n; ++v)
+    if (cost[v] < MAX_COST) seeds.push_back(label[v]);
+  std::sort(seeds.begin(), seeds.end());
+  seeds.erase(std::unique(seeds.begin(), seeds.end()), seeds.end());
+  const i64 S = (i64)seeds.size();
+  auto ord = [&](u32 s) { return (i64)(std::lower_bound(seeds.begin(), seeds.end(), s) - seeds.begin()); };
+  std::vector<i64> parent((size_t)S);
+  std::iota(parent.begin(), parent.end(), 0);
+  std::function<i64(i64)> find = [&](i64 x) { return parent[x] == x ? x : parent[x] = find(parent[x]); };
+  std::vector<i64> order((size_t)m);
+  std::iota(order.begin(), order.end(), 0);
+  std::sort(order.begin(), order.end(), [&](i64 i, i64 j) {
+    if (saddle[i] != saddle[j]) return saddle[i] < saddle[j];
+    if (ra[i] != ra[j]) return ra[i] < ra[j];
+    return rb[i] < rb[j];
+  });
+  i64 clusters = S;
+  for (i64 idx : order) {
+    if (clusters <= (i64)num_regions) break;
+    i64 a = find(ord(ra[idx])), b = find(ord(rb[idx]));
+    if (a == b) continue;
+    if (a < b) parent[b] = a;  // root = smallest ordinal = smallest seed id
+    else parent[a] = b;
+    --clusters;
+  }
+  for (i64 v = 0; v < n; ++v)
+    cluster_of[v] = cost[v] < MAX_COST ? seeds[(size_t)find(ord(label[v]))] : 0xFFFFFFFFu;
+  return clusters;
+}
+
+// The literal Cluster of cluster.hpp:23-229 fed by the literal MST of ift.hpp:207-243,
+// vertex ids standing in for addresses.  Informational: quirks kept — the region-id
+// rewrite of create_TLC acts on a COPY of the heap's container and has no effect
+// (cluster.hpp:100-108); single_linking only ever merges while the first key has a partner
+// (its inner iterator is never rewound, cluster.hpp:174-195).  Guards (App. B #10): returns
+// -1 when TLC.size() <= num_regions or the distance map empties.
+// region_of[v] = index into the final `regions` list, or -1.
+ORC_API i64 orc_cluster_literal(i64 n, const u32* label, const u32* mst_a, const u32* mst_b, const double* mst_w,
+                                i64 m, int num_regions, int32_t* region_of) {
+  // root_translator: first-appearance order over the vertex-ordered root map (cluster.hpp:85-89)
+  std::map<u32, int> translator;
+  int counter = 0;
+  for (i64 v = 0; v < n; ++v)
+    if (translator.find(label[v]) == translator.end()) translator[label[v]] = counter++;
+  struct Edge {
+    int r1, r2;
+    double w;
+  };
+  auto cmp = [](const Edge& a, const Edge& b) { return a.w > b.w; };
+  std::priority_queue<Edge, std::vector<Edge>, decltype(cmp)> pq(cmp);
+  // the reference's std::map is ordered by (s_root, r_root)
+  std::vector<i64> eo((size_t)m);
+  std::iota(eo.begin(), eo.end(), 0);
+  std::sort(eo.begin(), eo.end(), [&](i64 i, i64 j) {
+    return mst_a[i] != mst_a[j] ? mst_a[i] < mst_a[j] : mst_b[i] < mst_b[j];
+  });
+  for (i64 i : eo) pq.push(Edge{translator[mst_a[i]], translator[mst_b[i]], mst_w[i]});
+  std::vector<Edge> tlc;
+  while (!pq.empty()) {
+    tlc.push_back(pq.top());
+    pq.pop();
+  }
+  for (i64 v = 0; v < n; ++v) region_of[v] = -1;
+  if ((i64)tlc.size() <= (i64)num_regions || tlc.size() < 2) return -1;
+  typedef std::set<int> Key;
+  std::map<Key, double> dist;
+  for (int i = 0; i < (int)tlc.size(); ++i)
+    for (int j = i + 1; j < (int)tlc.size(); ++j) dist[Key{i, j}] = std::sqrt(std::pow(tlc[i].w - tlc[j].w, 2));
+  auto shares = [](const Key& a, const Key& b) {
+    for (int x : a)
+      if (b.count(x)) return true;
+    return false;
+  };
+  auto minus = [](const Key& a, const Key& k) {
+    Key r;
+    std::set_difference(a.begin(), a.end(), k.begin(), k.end(), std::inserter(r, r.begin()));
+    return r;
+  };
+  for (size_t it = 0; it < tlc.size() - (size_t)num_regions; ++it) {
+    if (dist.empty()) return -1;
+    Key key;
+    double best = INFINITY;
+    for (auto& kv : dist)
+      if (kv.second < best) {
+        key = kv.first;
+        best = kv.second;
+      }
+    std::vector<Key> keys;
+    for (auto& kv : dist)
+      if (shares(key, kv.first) && kv.first != key) keys.push_back(kv.first);
+    // only the first key ever finds partners; both iterators restart after a merge
+    size_t i2 = 0;
+    while (!keys.empty() && i2 < keys.size()) {
+      if (minus(keys[0], key) == minus(keys[i2], key) && keys[0] != keys[i2]) {
+        Key a = keys[0], b = keys[i2];
+        if (!(dist[a] < dist[b])) std::swap(a, b);
+        double wgt = dist[a];
+        Key merged = a;
+        merged.insert(key.begin(), key.end());
+        dist[merged] = wgt;
+        dist.erase(b);
+        dist.erase(a);
+        keys.erase(keys.begin() + (long)i2);
+        keys.erase(keys.begin());
+        i2 = 0;
+      } else {
+        ++i2;
+      }
+    }
+    dist.erase(key);
+  }
+  if (dist.empty()) return -1;
+  std::vector<Key> regions;
+  regions.push_back(dist.begin()->first);
+  for (auto& kv : dist) {
+    const Key& k = kv.first;
+    if (k != regions[0] && shares(k, regions[0]) && regions.size() == 1) {
+      Key r1, r2, r3;
+      std::set_intersection(k.begin(), k.end(), regions[0].begin(), regions[0].end(), std::inserter(r1, r1.begin()));
+      r2 = minus(regions[0], r1);
+      r3 = minus(k, r1);
+      regions.push_back(r1);
+      regions.push_back(r2);
+      regions.push_back(r3);
+      regions.erase(regions.begin());
+    } else if (shares(k, regions[0]) && regions.size() > 1) {
+      regions.push_back(minus(k, regions[0]));
+    }
+  }
+  // getLabelCloud (cluster.hpp:54-79): root -> first TLC entry naming it -> first region holding that entry
+  for (i64 v = 0; v < n; ++v) {
+    int r = translator[label[v]];
+    int tlc_idx = -1;
+    for (int i = 0; i < (int)tlc.size(); ++i)
+      if (r == tlc[i].r1 || r == tlc[i].r2) {
+        tlc_idx = i;
+        break;
+      }
+    if (tlc_idx < 0) continue;
+    for (int c = 0; c < (int)regions.size(); ++c)
+      if (regions[c].count(tlc_idx)) {
+        region_of[v] = c;
+        break;
+      }
+  }
+  return (i64)regions.size();
 }

@@ -213,3 +213,61 @@ def regmin(off, adj, inten):
     lib().orc_regmin.restype = C.c_int64
     m = int(lib().orc_regmin(_p(off), _p(adj), C.c_int64(len(inten)), _p(inten), _p(seeds)))
     return seeds[:m].copy()
+
+
+def region_adjacency(off, adj, cost, label):
+    off = np.ascontiguousarray(off, np.uint32)
+    adj = np.ascontiguousarray(adj, np.uint32)
+    cost = np.ascontiguousarray(cost, np.uint32)
+    label = np.ascontiguousarray(label, np.uint32)
+    n = len(cost)
+    f = lib().orc_region_adjacency
+    f.restype = C.c_int64
+    m = int(f(_p(off), _p(adj), C.c_int64(n), _p(cost), _p(label), None, None, None, C.c_int64(0)))
+    a = np.empty(m, np.uint32)
+    b = np.empty(m, np.uint32)
+    s = np.empty(m, np.uint32)
+    f(_p(off), _p(adj), C.c_int64(n), _p(cost), _p(label), _p(a), _p(b), _p(s), C.c_int64(m))
+    return a, b, s
+
+
+def region_info(w, cost, label):
+    w = np.ascontiguousarray(w, np.float32)
+    cost = np.ascontiguousarray(cost, np.uint32)
+    label = np.ascontiguousarray(label, np.uint32)
+    n = len(cost)
+    f = lib().orc_region_info
+    f.restype = C.c_int64
+    m = int(f(C.c_int64(n), _p(w), _p(cost), _p(label), None, None, None, C.c_int64(0)))
+    seed = np.empty(m, np.uint32)
+    area = np.empty(m, np.uint32)
+    height = np.empty(m, np.float32)
+    f(C.c_int64(n), _p(w), _p(cost), _p(label), _p(seed), _p(area), _p(height), C.c_int64(m))
+    return seed, area, height
+
+
+def cluster_saddle(cost, label, ra, rb, saddle, num_regions):
+    cost = np.ascontiguousarray(cost, np.uint32)
+    label = np.ascontiguousarray(label, np.uint32)
+    ra = np.ascontiguousarray(ra, np.uint32)
+    rb = np.ascontiguousarray(rb, np.uint32)
+    saddle = np.ascontiguousarray(saddle, np.uint32)
+    out = np.empty(len(cost), np.uint32)
+    f = lib().orc_cluster_saddle
+    f.restype = C.c_int64
+    k = int(f(C.c_int64(len(cost)), _p(cost), _p(label), _p(ra), _p(rb), _p(saddle), C.c_int64(len(ra)),
+              C.c_int(num_regions), _p(out)))
+    return out, k
+
+
+def cluster_literal(label, mst_a, mst_b, mst_w, num_regions):
+    label = np.ascontiguousarray(label, np.uint32)
+    mst_a = np.ascontiguousarray(mst_a, np.uint32)
+    mst_b = np.ascontiguousarray(mst_b, np.uint32)
+    mst_w = np.ascontiguousarray(mst_w, np.float64)
+    out = np.empty(len(label), np.int32)
+    f = lib().orc_cluster_literal
+    f.restype = C.c_int64
+    k = int(f(C.c_int64(len(label)), _p(label), _p(mst_a), _p(mst_b), _p(mst_w), C.c_int64(len(mst_a)),
+              C.c_int(num_regions), _p(out)))
+    return out, k
