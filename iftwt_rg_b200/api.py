@@ -95,6 +95,9 @@ def load_library(build_if_missing: bool = True):
     lib.iftwt_region_adjacency.argtypes = [vp, vp, vp, vp, sz, C.POINTER(sz)]
     lib.iftwt_region_info.argtypes = [vp, vp, vp, vp, sz, C.POINTER(sz)]
     lib.iftwt_cluster.argtypes = [vp, i32, vp, C.POINTER(sz)]
+    lib.iftwt_knn_device.argtypes = [vp, i32, vp, vp]
+    lib.iftwt_normals_device.argtypes = [vp, i32, vp]
+    lib.iftwt_set_knn_rows_device.argtypes = [vp, i32, vp, vp]
     lib.iftwt_stage_ms.argtypes = [vp, i32, C.POINTER(f32)]
     lib.iftwt_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.iftwt_reset_counters.argtypes = [vp]
@@ -274,6 +277,16 @@ class Context:
         if ns.value:
             self._check(self._lib.iftwt_regmin_seeds(self._h, _ptr(seeds), ns.value, C.byref(ns)))
         return seeds
+
+    # -- device-pointer variants (multi-GPU plumbing) --------------------------
+    def knn_device(self, k: int, d_idx: int, d_d2: int = 0):
+        self._check(self._lib.iftwt_knn_device(self._h, k, C.c_void_p(d_idx), C.c_void_p(d_d2) if d_d2 else None))
+
+    def normals_device(self, k: int, d_out4: int):
+        self._check(self._lib.iftwt_normals_device(self._h, k, C.c_void_p(d_out4)))
+
+    def set_knn_rows_device(self, k: int, d_idx: int, d_d2: int):
+        self._check(self._lib.iftwt_set_knn_rows_device(self._h, k, C.c_void_p(d_idx), C.c_void_p(d_d2)))
 
     # -- region hierarchy ------------------------------------------------------
     def region_adjacency(self):

@@ -64,6 +64,23 @@ __global__ void set_intensity_kernel(const float* __restrict__ v, u32 n, float4*
   if (i < n) pts[i].w = v[i];
 }
 
+// externally computed rows (original ids) -> the ctx's sorted-space lists
+__global__ void install_rows_kernel(const int* __restrict__ idx_o, const float* __restrict__ d2_o,
+                                    const u32* __restrict__ perm, const u32* __restrict__ inv, u32 n, int k,
+                                    u32* __restrict__ nbr, float* __restrict__ nd2, u64* __restrict__ kth) {
+  const u32 s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (s >= n) return;
+  const u32 o = perm[s];
+  for (int j = lane; j < k; j += 32) {
+    int v = idx_o[(size_t)o * k + j];
+    float d = d2_o[(size_t)o * k + j];
+    nbr[(size_t)s * k + j] = v < 0 ? SID_NONE : inv[v];
+    nd2[(size_t)s * k + j] = d;
+    if (j == k - 1) kth[s] = v < 0 ? 0xFFFFFFFFFFFFFFFFull : (((u64)__float_as_uint(d) << 32) | (u64)(u32)v);
+  }
+}
+
 int check_ctx(iftwt_ctx* c) {
   if (!c) {
     g_err = "null ctx";
@@ -504,6 +521,56 @@ int iftwt_cluster(iftwt_ctx* c, int num_regions, uint32_t* cluster_of, size_t* n
   ENSURE(c, c->out_b, c->n * 4);
   TRY(cluster_run(c, num_regions, c->out_b.as<u32>(), n_clusters));
   if (cluster_of) CU_TRY(c, cudaMemcpyAsync(cluster_of, c->out_b.p, c->n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return IFTWT_OK;
+}
+
+int iftwt_knn_device(iftwt_ctx* c, int k, int32_t* d_idx, float* d_d2) {
+  TRY(check_ctx(c));
+  if (!d_idx) return ctx_fail(c, IFTWT_ERR_INVALID, "null device output");
+  TRY(knn_run(c, k));
+  const size_t ne = c->n * (size_t)k;
+  LAUNCH(c, export_knn_kernel, div_up(ne, 256), 256, 0, c->nbr.as<u32>(), c->nd2.as<float>(), c->inv.as<u32>(),
+         c->perm.as<u32>(), ne, k, (int*)d_idx, d_d2);
+  CHECK_LAUNCH(c);
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  note_fallback(c);
+  return IFTWT_OK;
+}
+
+int iftwt_normals_device(iftwt_ctx* c, int k, float* d_out4) {
+  TRY(check_ctx(c));
+  if (!d_out4) return ctx_fail(c, IFTWT_ERR_INVALID, "null device output");
+  TRY(knn_run(c, k));
+  TRY(normals_run(c));
+  LAUNCH(c, export_normals_kernel, div_up(c->n, 256), 256, 0, c->nrm.as<float4>(), c->inv.as<u32>(), (u32)c->n,
+         (float4*)d_out4);
+  CHECK_LAUNCH(c);
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return IFTWT_OK;
+}
+
+int iftwt_set_knn_rows_device(iftwt_ctx* c, int k, const int32_t* d_idx, const float* d_d2) {
+  TRY(check_ctx(c));
+  if (c->n == 0) return ctx_fail(c, IFTWT_ERR_STATE, "no cloud set");
+  if (!d_idx || !d_d2 || k < 1 || k > 64) return ctx_fail(c, IFTWT_ERR_INVALID, "bad rows");
+  TRY(grid_build(c, k));
+  TRY(graph_detach_rows(c));
+  const size_t n = c->n;
+  ENSURE(c, c->nbr, n * k * 4);
+  ENSURE(c, c->nd2, n * k * 4);
+  ENSURE(c, c->kth, n * 8);
+  ENSURE(c, c->fb_list, n * 4);
+  LAUNCH(c, install_rows_kernel, div_up(n * 32, 256), 256, 0, (const int*)d_idx, d_d2, c->perm.as<u32>(),
+         c->inv.as<u32>(), (u32)n, k, c->nbr.as<u32>(), c->nd2.as<float>(), c->kth.as<u64>());
+  CHECK_LAUNCH(c);
+  c->knn_k = k;
+  c->mask_k = 0;
+  if (c->graph_kind == 1) {
+    c->graph_k = 0;
+    c->graph_kind = 0;
+  }
+  c->nrm_k = 0;
   CU_TRY(c, cudaStreamSynchronize(c->stream));
   return IFTWT_OK;
 }

@@ -231,6 +231,18 @@ IFTWT_API int iftwt_region_info(iftwt_ctx* ctx, uint32_t* seed, uint32_t* area, 
  * 0xFFFFFFFF for vertices the IFT never conquered. */
 IFTWT_API int iftwt_cluster(iftwt_ctx* ctx, int num_regions, uint32_t* cluster_of, size_t* n_clusters);
 
+/* ---- device-pointer variants (multi-GPU plumbing: the Morton-range sharded k-NN of
+ * iftwt_rg_b200/sharded.py keeps everything on the device between NCCL exchanges) -------- */
+
+/* iftwt_knn / iftwt_normals with DEVICE output buffers on ctx's device (rows in original
+ * index order; d_d2 may be NULL; d_out4 is packed float4 {nx,ny,nz,curvature}). */
+IFTWT_API int iftwt_knn_device(iftwt_ctx* ctx, int k, int32_t* d_idx, float* d_d2);
+IFTWT_API int iftwt_normals_device(iftwt_ctx* ctx, int k, float* d_out4);
+/* Install externally computed k-NN rows (DEVICE buffers, original indices, canonical order,
+ * -1 / +inf padded) as the ctx's current lists: the bridge from a sharded k-NN to the
+ * single-GPU graph / seeds / IFT stages.  The cloud must be set. */
+IFTWT_API int iftwt_set_knn_rows_device(iftwt_ctx* ctx, int k, const int32_t* d_idx, const float* d_d2);
+
 /* Instrumentation (the reference's is one std::time pair, ift.hpp:172-173). */
 IFTWT_API int iftwt_stage_ms(iftwt_ctx* ctx, int stage, float* ms); /* CUDA-event time of the last run of a stage */
 IFTWT_API int iftwt_get_stats(iftwt_ctx* ctx, iftwt_stats* out);
