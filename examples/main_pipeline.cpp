@@ -58,13 +58,14 @@ int main(int argc, char** argv) {
     normal_estimator.compute(normals);
 
     FlatPoint<global::PointI, iftwt::types::Normal> reg(gg);                     // main.cpp:111-119
-    reg.setMinClusterSize(50);
-    reg.setMaxClusterSize(10000);
+    reg.setMinClusterSize(20);
+    reg.setMaxClusterSize(100000);
     reg.setNumberOfNeighbours(50);
-    reg.setSmoothnessThreshold(12.0f / 180.0f * 3.14159265f);
+    reg.setSmoothnessThreshold(20.0f / 180.0f * 3.14159265f);
     reg.setCurvatureThreshold(1.0f);
     global::Cloud::Ptr centroid_cloud = reg.getCentroidsCloud();                 // main.cpp:121
 
+    if (centroid_cloud->size() == 0) std::printf("no region-growing seeds: try IFT_PCD ift(gg) (regional minima)\n");
     IFT_PCD ift(gg, centroid_cloud);                                             // main.cpp:123
     Cluster c(ift, 10);                                                          // main.cpp:124
 

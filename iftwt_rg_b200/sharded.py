@@ -156,6 +156,8 @@ def gpu_local_knn(ctx):
     """local_knn hook backed by libiftwt.so on the rank's GPU."""
     def run(local_pts: torch.Tensor, k: int, want_normals: bool):
         n = local_pts.shape[0]
+        # the ctx runs on its own stream: everything torch queued for these tensors must be done
+        torch.cuda.current_stream(local_pts.device).synchronize()
         ctx.set_cloud_device(local_pts.data_ptr(), n)
         idx = torch.empty((n, k), dtype=torch.int32, device=local_pts.device)
         d2 = torch.empty((n, k), dtype=torch.float32, device=local_pts.device)

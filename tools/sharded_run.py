@@ -77,6 +77,7 @@ def main():
     if rank == 0:
         all_pts, all_idx, all_d2 = gathered
         if not args.no_ift:
+            torch.cuda.synchronize()   # the ctx has its own stream
             t1 = time.perf_counter()
             ctx.set_cloud_device(all_pts.data_ptr(), n)
             ctx.set_knn_rows_device(k, all_idx.data_ptr(), all_d2.data_ptr())
@@ -88,6 +89,7 @@ def main():
             out["rank0_graph_seeds_ift_s"] = time.perf_counter() - t1
             out["stats"] = {kk: v for kk, v in ctx.stats().items() if kk in ("n_arcs", "n_seeds", "ift_levels")}
         if args.verify:
+            torch.cuda.synchronize()
             c2 = api.Context(local)
             c2.set_cloud_device(all_pts.data_ptr(), n)
             vi = torch.empty((n, k), dtype=torch.int32, device=dev)
