@@ -87,6 +87,7 @@ struct iftwt_ctx {
   bool seeds_valid = false;
   // --- ift ---
   DevBuf ift_state, ift_parent, ift_w, ift_byw, ift_local;
+  DevBuf ift_info; // u64 [n] FINAL | weight << 32 | label: one gather per arc visit
   DevBuf ift_res;  // u64 [n] resolved (cost << 32 | label) per sorted vertex
   DevBuf ift_wf;   // float [n] the weights the IFT ran on, sorted space
   // --- hierarchy ---

@@ -28,11 +28,20 @@
 // is what makes the labels schedule independent (SURVEY finding 6); inside a level
 // nothing depends on thread order.
 #include <cub/cub.cuh>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
 #define W_CLOSED 511u  // weight >= MAX_COST: the vertex can never be conquered
 #define LBL_NONE 0xFFFFFFFFu
+// info[v] = FINAL | weight << 32 | label: everything a neighbour needs from v in ONE 8-byte
+// gather.  FINAL is set (with the component's label) once v's component is conquered — by the
+// finalize blocks that ride along with the next level's launch, or lazily by the first
+// visitor that resolves v through the union-find.  A conquered component never changes, so
+// every writer stores the same word.
+#define INFO_FINAL 0x8000000000000000ull
+#define INFO_W(e) ((u32)((e) >> 32) & 0x1FFu)
 
 namespace {
 
@@ -64,7 +73,7 @@ __device__ __forceinline__ void uf_union_roots(u32* parent, u32 ra, u32 rb) {
 __global__ void ift_init_kernel(const float* __restrict__ w_orig, const float4* __restrict__ pts_in,
                                 const u32* __restrict__ perm, u32 n, unsigned short* __restrict__ w16,
                                 u64* __restrict__ state, u32* __restrict__ parent, u32* __restrict__ ids,
-                                float* __restrict__ wf, u32* __restrict__ bad) {
+                                float* __restrict__ wf, u64* __restrict__ info, u32* __restrict__ bad) {
   u32 v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n) return;
   u32 o = perm[v];
@@ -78,13 +87,14 @@ __global__ void ift_init_kernel(const float* __restrict__ w_orig, const float4* 
     q = w >= (float)IFTWT_MAX_COST ? (unsigned short)W_CLOSED : (unsigned short)w;
   }
   w16[v] = q;
+  info[v] = ((u64)q << 32) | (u64)LBL_NONE;
   state[v] = ((u64)IFTWT_MAX_COST << 32) | (u64)o;
   parent[v] = v;
   ids[v] = v;
 }
 __global__ void ift_seed_kernel(const u32* __restrict__ seeds_orig, u32 ns, const u32* __restrict__ inv, u32 n,
                                 unsigned short* __restrict__ w16, u64* __restrict__ state,
-                                u32* __restrict__ bad) {
+                                u64* __restrict__ info, u32* __restrict__ bad) {
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ns) return;
   u32 o = seeds_orig[i];
@@ -95,6 +105,7 @@ __global__ void ift_seed_kernel(const u32* __restrict__ seeds_orig, u32 ns, cons
   u32 v = inv[o];
   w16[v] = 0;            // open from level 0 on; its own value never matters (ift.hpp:138)
   state[v] = (u64)o;     // cost 0, label = itself
+  info[v] = INFO_FINAL | (u64)o;
 }
 // seg_off[c] = first position in the weight-sorted vertex list with weight >= c, c = 0..512
 __global__ void ift_segments_kernel(const unsigned short* __restrict__ w_sorted, u32 n, u32* __restrict__ seg_off) {
@@ -111,35 +122,54 @@ __global__ void ift_segments_kernel(const unsigned short* __restrict__ w_sorted,
 
 // A: one warp per newly opened vertex.  adjacency(t) = its k-NN row + its reverse arcs.
 struct OpenCtx {
-  const unsigned short* w16;
+  u64* info;
   const u64* state;
   u32* parent;
   u32 level;
 };
 __device__ __forceinline__ void ift_visit(const OpenCtx& x, u32 t, u32 u, u32& lmin) {
-  if ((u32)x.w16[u] > x.level) return;  // closed at this level
-  u32 ru = uf_find(x.parent, u);
-  u64 su = x.state[ru];
+  const u64 e = x.info[u];
+  if (e & INFO_FINAL) {  // conquered neighbour: an entry offer at cost `level`
+    lmin = min(lmin, (u32)e);
+    return;
+  }
+  if (INFO_W(e) > x.level) return;  // closed at this level
+  const u32 ru = uf_find(x.parent, u);
+  const u64 su = x.state[ru];
   if ((u32)(su >> 32) < IFTWT_MAX_COST) {
-    lmin = min(lmin, (u32)su);  // conquered neighbour: an entry offer at cost `level`
+    lmin = min(lmin, (u32)su);
+    x.info[u] = INFO_FINAL | (e & 0x000001FF00000000ull) | (u64)(u32)su;  // lazy finalize
   } else {
     uf_union_roots(x.parent, uf_find(x.parent, t), ru);
   }
 }
+// Blocks [0, open_blocks) open the vertices of this level's segment; the remaining blocks
+// finalize the previous level's segment (one thread per vertex) — independent work that would
+// otherwise need a launch of its own.
 __global__ void __launch_bounds__(256)
-ift_level_open_kernel(const u32* __restrict__ byw, u32 seg_begin, u32 seg_len, u32 level,
-                      const u32* __restrict__ fwd, int k, const u32* __restrict__ roff,
-                      const u32* __restrict__ radj, const unsigned short* __restrict__ w16,
+ift_level_open_kernel(const u32* __restrict__ byw, u32 seg_begin, u32 seg_len, u32 level, u32 open_blocks,
+                      u32 prev_begin, u32 prev_len, const u32* __restrict__ fwd, int k,
+                      const u32* __restrict__ roff, const u32* __restrict__ radj, u64* __restrict__ info,
                       const u64* __restrict__ state, u32* __restrict__ parent, u32* __restrict__ local_min) {
+  if (blockIdx.x >= open_blocks) {
+    const u32 i = (blockIdx.x - open_blocks) * blockDim.x + threadIdx.x;
+    if (i >= prev_len) return;
+    const u32 t = byw[prev_begin + i];
+    const u64 e = info[t];
+    if (e & INFO_FINAL) return;
+    const u64 s = state[uf_find(parent, t)];
+    if ((u32)(s >> 32) < IFTWT_MAX_COST) info[t] = INFO_FINAL | (e & 0x000001FF00000000ull) | (u64)(u32)s;
+    return;
+  }
   const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (gw >= seg_len) return;
   const u32 t = byw[seg_begin + gw];
-  if ((u32)(state[t] >> 32) < IFTWT_MAX_COST) {  // a seed: conquered from the start
+  if (info[t] & INFO_FINAL) {  // a seed: conquered from the start
     if (lane == 0) local_min[t] = LBL_NONE;
     return;
   }
-  OpenCtx x{w16, state, parent, level};
+  OpenCtx x{info, state, parent, level};
   u32 lmin = LBL_NONE;
   for (int j = lane; j < k; j += 32) {
     u32 u = fwd[(size_t)t * k + j];
@@ -192,6 +222,8 @@ int ift_run(iftwt_ctx* c, const float* d_w_orig, const u32* d_seeds_orig, size_t
   ENSURE(c, c->ift_local, (size_t)n * 4);
   ENSURE(c, c->ift_res, (size_t)n * 8);
   ENSURE(c, c->ift_wf, (size_t)n * 4);
+  ENSURE(c, c->ift_info, (size_t)n * 8);
+  u64* info = c->ift_info.as<u64>();
   ENSURE(c, c->out_a, (size_t)n * 4 * 2);
   u64* state = c->ift_state.as<u64>();
   u32* parent = c->ift_parent.as<u32>();
@@ -206,9 +238,9 @@ int ift_run(iftwt_ctx* c, const float* d_w_orig, const u32* d_seeds_orig, size_t
   u32* d_seg = sc + 128;  // 513 entries
   CU_TRY(c, cudaMemsetAsync(d_bad, 0, 8, c->stream));
   LAUNCH(c, ift_init_kernel, div_up(n, 256), 256, 0, d_w_orig, c->pts_in.as<float4>(), c->perm.as<u32>(), n, w16,
-         state, parent, ids, c->ift_wf.as<float>(), d_bad);
+         state, parent, ids, c->ift_wf.as<float>(), info, d_bad);
   if (ns) LAUNCH(c, ift_seed_kernel, div_up(ns, 256), 256, 0, d_seeds_orig, (u32)ns, c->inv.as<u32>(), n, w16,
-                 state, d_bad);
+                 state, info, d_bad);
   CHECK_LAUNCH(c);
   {  // vertices grouped by weight (stable: ascending vertex id inside a level)
     size_t tb = 0;
@@ -228,13 +260,17 @@ int ift_run(iftwt_ctx* c, const float* d_w_orig, const u32* d_seeds_orig, size_t
   const u32* seg = hs + 128;
   const u32* fwd = c->graph_shares_nbr ? c->nbr.as<u32>() : c->g_fwd.as<u32>();
   u64 levels = 0;
+  u32 prev_b = 0, prev_len = 0;
   for (u32 lv = 0; lv < IFTWT_MAX_COST; ++lv) {
     u32 b = seg[lv], len = seg[lv + 1] - seg[lv];
     if (len == 0) continue;
     ++levels;
-    LAUNCH(c, ift_level_open_kernel, div_up((size_t)len * 32, 256), 256, 0, byw, b, len, lv, fwd, c->graph_k,
-           c->g_off.as<u32>(), c->g_adj.as<u32>(), w16, state, parent, local_min);
+    const u32 open_blocks = div_up((size_t)len * 32, 256);
+    LAUNCH(c, ift_level_open_kernel, open_blocks + div_up(prev_len, 256), 256, 0, byw, b, len, lv, open_blocks, prev_b,
+           prev_len, fwd, c->graph_k, c->g_off.as<u32>(), c->g_adj.as<u32>(), info, state, parent, local_min);
     LAUNCH(c, ift_level_settle_kernel, div_up(len, 256), 256, 0, byw, b, len, lv, parent, local_min, state);
+    prev_b = b;
+    prev_len = len;
   }
   CHECK_LAUNCH(c);
   u32* cost_o = c->out_a.as<u32>();
