@@ -55,20 +55,6 @@ __device__ __forceinline__ u32 uf_find(u32* parent, u32 v) {
   }
   return v;
 }
-__device__ __forceinline__ void uf_union_roots(u32* parent, u32 ra, u32 rb) {
-  while (ra != rb) {
-    if (ra < rb) {
-      u32 ret = atomicCAS(&parent[rb], rb, ra);
-      if (ret == rb) return;
-      rb = ret;
-    } else {
-      u32 ret = atomicCAS(&parent[ra], ra, rb);
-      if (ret == ra) return;
-      ra = ret;
-    }
-  }
-}
-
 // weights (original order) -> u16 per sorted vertex; flags non-integer / negative input
 __global__ void ift_init_kernel(const float* __restrict__ w_orig, const float4* __restrict__ pts_in,
                                 const u32* __restrict__ perm, u32 n, unsigned short* __restrict__ w16,
@@ -127,20 +113,35 @@ struct OpenCtx {
   u32* parent;
   u32 level;
 };
-__device__ __forceinline__ void ift_visit(const OpenCtx& x, u32 t, u32 u, u32& lmin) {
+// rt = this lane's belief of t's representative (t itself until a hook says otherwise); a stale
+// belief only costs a failed CAS, which returns the way up.
+__device__ __forceinline__ void ift_visit(const OpenCtx& x, u32& rt, u32 u, u32& lmin) {
   const u64 e = x.info[u];
   if (e & INFO_FINAL) {  // conquered neighbour: an entry offer at cost `level`
     lmin = min(lmin, (u32)e);
     return;
   }
   if (INFO_W(e) > x.level) return;  // closed at this level
-  const u32 ru = uf_find(x.parent, u);
+  u32 ru = uf_find(x.parent, u);
   const u64 su = x.state[ru];
   if ((u32)(su >> 32) < IFTWT_MAX_COST) {
     lmin = min(lmin, (u32)su);
     x.info[u] = INFO_FINAL | (e & 0x000001FF00000000ull) | (u64)(u32)su;  // lazy finalize
-  } else {
-    uf_union_roots(x.parent, uf_find(x.parent, t), ru);
+    return;
+  }
+  while (rt != ru) {  // hook the larger representative under the smaller
+    if (rt < ru) {
+      const u32 ret = atomicCAS(&x.parent[ru], ru, rt);
+      if (ret == ru) break;
+      ru = ret;
+    } else {
+      const u32 ret = atomicCAS(&x.parent[rt], rt, ru);
+      if (ret == rt) {
+        rt = ru;
+        break;
+      }
+      rt = ret;
+    }
   }
 }
 // Blocks [0, open_blocks) open the vertices of this level's segment; the remaining blocks
@@ -171,12 +172,13 @@ ift_level_open_kernel(const u32* __restrict__ byw, u32 seg_begin, u32 seg_len, u
   }
   OpenCtx x{info, state, parent, level};
   u32 lmin = LBL_NONE;
+  u32 rt = t;
   for (int j = lane; j < k; j += 32) {
     u32 u = fwd[(size_t)t * k + j];
-    if (u != 0xFFFFFFFFu && u != t) ift_visit(x, t, u, lmin);
+    if (u != 0xFFFFFFFFu && u != t) ift_visit(x, rt, u, lmin);
   }
   const u32 b = roff[t], e = roff[t + 1];
-  for (u32 a = b + lane; a < e; a += 32) ift_visit(x, t, radj[a], lmin);
+  for (u32 a = b + lane; a < e; a += 32) ift_visit(x, rt, radj[a], lmin);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
   if (lane == 0) local_min[t] = lmin;
