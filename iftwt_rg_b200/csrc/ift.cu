@@ -144,9 +144,15 @@ __device__ __forceinline__ void ift_visit(const OpenCtx& x, u32& rt, u32 u, u32&
     }
   }
 }
-// Blocks [0, open_blocks) open the vertices of this level's segment; the remaining blocks
-// finalize the previous level's segment (one thread per vertex) — independent work that would
-// otherwise need a launch of its own.
+// Blocks [0, open_blocks) open the vertices of this level's segment, G lanes per vertex; the
+// remaining blocks finalize the previous level's segment (one thread per vertex) — independent
+// work that would otherwise need a launch of its own.
+// Why G varies: a vertex visit is a chain of ~7 dependent memory accesses, so a level's time is
+// (vertices in flight)^-1 x chain latency, not bandwidth.  With a whole warp per vertex only
+// 64 x 148 vertices are in flight; big levels use fewer lanes per vertex (down to one thread
+// per vertex) to put up to 32x more chains in flight, small levels keep a warp per vertex so
+// that each chain is as short as possible.
+template <int G>
 __global__ void __launch_bounds__(256)
 ift_level_open_kernel(const u32* __restrict__ byw, u32 seg_begin, u32 seg_len, u32 level, u32 open_blocks,
                       u32 prev_begin, u32 prev_len, const u32* __restrict__ fwd, int k,
@@ -162,26 +168,29 @@ ift_level_open_kernel(const u32* __restrict__ byw, u32 seg_begin, u32 seg_len, u
     if ((u32)(s >> 32) < IFTWT_MAX_COST) info[t] = INFO_FINAL | (e & 0x000001FF00000000ull) | (u64)(u32)s;
     return;
   }
-  const u32 gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (gw >= seg_len) return;
-  const u32 t = byw[seg_begin + gw];
-  if (info[t] & INFO_FINAL) {  // a seed: conquered from the start
-    if (lane == 0) local_min[t] = LBL_NONE;
-    return;
+  const u32 gv = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const int gl = threadIdx.x % G;
+  const bool active = gv < seg_len;
+  u32 t = 0;
+  bool work = false;
+  if (active) {
+    t = byw[seg_begin + gv];
+    work = !(info[t] & INFO_FINAL);  // a seed is conquered from the start
   }
-  OpenCtx x{info, state, parent, level};
   u32 lmin = LBL_NONE;
-  u32 rt = t;
-  for (int j = lane; j < k; j += 32) {
-    u32 u = fwd[(size_t)t * k + j];
-    if (u != 0xFFFFFFFFu && u != t) ift_visit(x, rt, u, lmin);
+  if (work) {
+    OpenCtx x{info, state, parent, level};
+    u32 rt = t;
+    for (int j = gl; j < k; j += G) {
+      u32 u = fwd[(size_t)t * k + j];
+      if (u != 0xFFFFFFFFu && u != t) ift_visit(x, rt, u, lmin);
+    }
+    const u32 b = roff[t], e = roff[t + 1];
+    for (u32 a = b + gl; a < e; a += G) ift_visit(x, rt, radj[a], lmin);
   }
-  const u32 b = roff[t], e = roff[t + 1];
-  for (u32 a = b + lane; a < e; a += 32) ift_visit(x, rt, radj[a], lmin);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
-  if (lane == 0) local_min[t] = lmin;
+  for (int o = G / 2; o > 0; o >>= 1) lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+  if (active && gl == 0) local_min[t] = lmin;
 }
 // B: push the entry labels to the component roots
 __global__ void ift_level_settle_kernel(const u32* __restrict__ byw, u32 seg_begin, u32 seg_len, u32 level,
@@ -263,12 +272,20 @@ int ift_run(iftwt_ctx* c, const float* d_w_orig, const u32* d_seeds_orig, size_t
   const u32* fwd = c->graph_shares_nbr ? c->nbr.as<u32>() : c->g_fwd.as<u32>();
   u64 levels = 0;
   u32 prev_b = 0, prev_len = 0;
+  const char* wenv = getenv("IFTWT_IFT_WAVES");
+  const double waves = wenv ? atof(wenv) : 4.0;  // swept on B200: 0.5 -> 10.4 ms, 2 -> 7.9, 4 -> 7.6, 8 -> 8.0, warp per vertex -> 9.5
   for (u32 lv = 0; lv < IFTWT_MAX_COST; ++lv) {
     u32 b = seg[lv], len = seg[lv + 1] - seg[lv];
     if (len == 0) continue;
     ++levels;
-    const u32 open_blocks = div_up((size_t)len * 32, 256);
-    LAUNCH(c, ift_level_open_kernel, open_blocks + div_up(prev_len, 256), 256, 0, byw, b, len, lv, open_blocks, prev_b,
+    // lanes per vertex: keep about two waves of threads in flight
+    int G = 32;
+    while (G > 1 && (double)len * G > waves * 2048.0 * (double)c->sm_count) G >>= 1;
+    const u32 open_blocks = div_up((size_t)len * G, 256);
+    auto kern = G == 32 ? ift_level_open_kernel<32> : G == 16 ? ift_level_open_kernel<16>
+              : G == 8 ? ift_level_open_kernel<8> : G == 4 ? ift_level_open_kernel<4>
+              : G == 2 ? ift_level_open_kernel<2> : ift_level_open_kernel<1>;
+    LAUNCH(c, kern, open_blocks + div_up(prev_len, 256), 256, 0, byw, b, len, lv, open_blocks, prev_b,
            prev_len, fwd, c->graph_k, c->g_off.as<u32>(), c->g_adj.as<u32>(), info, state, parent, local_min);
     LAUNCH(c, ift_level_settle_kernel, div_up(len, 256), 256, 0, byw, b, len, lv, parent, local_min, state);
     prev_b = b;
