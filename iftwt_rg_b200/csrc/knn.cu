@@ -25,7 +25,12 @@
 #include "common.cuh"
 
 #define KNN_WARPS 8
-#define KNN_CAP 256  // staged candidates per warp (8 per lane)
+#define KNN_CAP_OF(E) ((E) <= 2 ? 256 : 512)  // staged candidates per warp
+// Two compile-time round counts per E: the common case and the full buffer.  (Eight variants
+// made 9,144 SASS instructions and the kernel stalled on instruction fetch: ncu no_instruction
+// 4.2 per issue, profiles/r01_knn_cell_kernel_v3_ncu_full.txt.)
+#define KNN_RR_SMALL(E) ((E) == 1 ? 3 : (E) == 2 ? 5 : 10)
+#define KNN_RR_MAX(E) (KNN_CAP_OF(E) / 32)
 #define KEY_MAX 0xFFFFFFFFFFFFFFFFull
 #define SID_NONE 0xFFFFFFFFu
 
@@ -193,7 +198,8 @@ __device__ __forceinline__ void cell_queries(const CellWarp& w, const float* __r
     } else {
       tau = tau0;
     }
-    if (!done && lane == 0) fb_list[atomicAdd(fb_count, 1u)] = qid;
+    // bit 31: the one-ring block is known to be too small, the general path starts at stage 1
+    if (!done && lane == 0) fb_list[atomicAdd(fb_count, 1u)] = ok ? (qid | 0x80000000u) : qid;
   }
 }
 
@@ -203,6 +209,7 @@ knn_cell_kernel(GridView g, const float4* __restrict__ spts, const float* __rest
                 float tau0, u32* __restrict__ nbr, float* __restrict__ nd2, u64* __restrict__ kth,
                 u32* __restrict__ fb_list, u32* __restrict__ fb_count) {
   constexpr int CS = 32 * E;
+  constexpr int KNN_CAP = KNN_CAP_OF(E);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* s_pts_all = (float4*)smem_raw;                        // [W][CAP] staged candidates
   u32* s_d2_all = (u32*)(s_pts_all + KNN_WARPS * KNN_CAP);      // [W][CS] survivor d2 bits (16 B aligned)
@@ -261,8 +268,11 @@ knn_cell_kernel(GridView g, const float4* __restrict__ spts, const float* __rest
       s_id[o + t] = s + t;
     }
   }
-  // unstaged slots of the last round must hold finite coordinates (they are masked, not skipped)
-  for (int t = M + lane; t < ((M + 31) & ~31); t += 32) s_pts[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // the compiled round count covers the staged rounds; unstaged slots it touches must hold
+  // finite coordinates (they are masked, not skipped)
+  const int R = (M + 31) >> 5;
+  const int RRu = R <= KNN_RR_SMALL(E) ? KNN_RR_SMALL(E) : KNN_RR_MAX(E);
+  for (int t = M + lane; t < RRu * 32; t += 32) s_pts[t] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncwarp();
 
   CellWarp w;
@@ -275,20 +285,10 @@ knn_cell_kernel(GridView g, const float4* __restrict__ spts, const float* __rest
   w.qs = qs;
   w.qn = qn;
   w.qoff = qoff;
-  switch ((M + 31) >> 5) {
-    case 1: cell_queries<E, 1>(w, qb2, k, tau0, nbr, nd2, kth, fb_list, fb_count, lane); break;
-    case 2: cell_queries<E, 2>(w, qb2, k, tau0, nbr, nd2, kth, fb_list, fb_count, lane); break;
-    case 3: cell_queries<E, 3>(w, qb2, k, tau0, nbr, nd2, kth, fb_list, fb_count, lane); break;
-    case 4: cell_queries<E, 4>(w, qb2, k, tau0, nbr, nd2, kth, fb_list, fb_count, lane); break;
-    case 5: cell_queries<E, 5>(w, qb2, k, tau0, nbr, nd2, kth, fb_list, fb_count, lane); break;
-    case 6: cell_queries<E, 6>(w, qb2, k, tau0, nbr, nd2, kth, fb_list, fb_count, lane); break;
-    case 7: cell_queries<E, 7>(w, qb2, k, tau0, nbr, nd2, kth, fb_list, fb_count, lane); break;
-    default: cell_queries<E, 8>(w, qb2, k, tau0, nbr, nd2, kth, fb_list, fb_count, lane); break;
-  }
+  if (R <= KNN_RR_SMALL(E)) cell_queries<E, KNN_RR_SMALL(E)>(w, qb2, k, tau0, nbr, nd2, kth, fb_list, fb_count, lane);
+  else cell_queries<E, KNN_RR_MAX(E)>(w, qb2, k, tau0, nbr, nd2, kth, fb_list, fb_count, lane);
 }
 
-// ---------------------------------------------------------------------------
-// lane-distributed sorted list, position p = r*32 + lane, ascending keys
 template <int RL>
 struct WarpTopK {
   u64 key[RL];
@@ -364,12 +364,15 @@ knn_general_kernel(GridView g, const float4* __restrict__ spts, const float4* __
   WarpTopK<RL> top;
   for (u32 it = gw; it < total; it += nw) {
     u32 row;
+    int j0 = 0;
     float4 Q;
     if (EXTERNAL) {
       row = it;
       Q = queries[it];
     } else {
       row = list[it];
+      j0 = (int)(row >> 31);
+      row &= 0x7FFFFFFFu;
       Q = spts[row];
     }
     const double vx = ((double)Q.x - g.ox) * g.inv_cell, vy = ((double)Q.y - g.oy) * g.inv_cell,
@@ -377,7 +380,7 @@ knn_general_kernel(GridView g, const float4* __restrict__ spts, const float4* __
     const int cx = min(g.dimx - 1, max(0, (int)floor(vx)));
     const int cy = min(g.dimy - 1, max(0, (int)floor(vy)));
     const int cz = min(g.dimz - 1, max(0, (int)floor(vz)));
-    for (int j = 0;; ++j) {
+    for (int j = j0;; ++j) {
       top.reset();
       const int sx = cx >> j, sy = cy >> j, sz = cz >> j;
       const int sdx = ((g.dimx - 1) >> j) + 1, sdy = ((g.dimy - 1) >> j) + 1, sdz = ((g.dimz - 1) >> j) + 1;
@@ -453,8 +456,8 @@ knn_general_kernel(GridView g, const float4* __restrict__ spts, const float4* __
 
 // ---------------------------------------------------------------------------
 static size_t cell_kernel_smem(int E) {
-  int CS = 32 * E;
-  return (size_t)KNN_WARPS * (KNN_CAP * 16 + KNN_CAP * 4 + CS * 4 + CS * 4) + KNN_WARPS * 4 + 16;
+  int CS = 32 * E, cap = KNN_CAP_OF(E);
+  return (size_t)KNN_WARPS * (cap * 16 + cap * 4 + CS * 4 + CS * 4) + KNN_WARPS * 4 + 16;
 }
 
 int knn_run(iftwt_ctx* c, int k) {
