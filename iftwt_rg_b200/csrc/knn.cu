@@ -22,6 +22,8 @@
 // cell*2^j (contiguous Morton-prefix ranges of the sorted cloud, found by binary
 // search in the cell table), keeps the k best in a lane-distributed sorted list,
 // and stops when the k-th distance is inside the scanned block.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 #define KNN_WARPS 8
@@ -57,6 +59,7 @@ __device__ __forceinline__ void count_lt(int& acc, u32 x, u32 key) {
 // per-round code carries no branches; E = survivor slots per lane (CS = 32 E).
 template <int E, int RR>
 __device__ __forceinline__ void cell_queries(const CellWarp& w, const float* __restrict__ qb2, int k, float tau0,
+                                             float margin,
                                              u32* __restrict__ nbr, float* __restrict__ nd2,
                                              u64* __restrict__ kth, u32* __restrict__ fb_list,
                                              u32* __restrict__ fb_count, int lane) {
@@ -64,9 +67,9 @@ __device__ __forceinline__ void cell_queries(const CellWarp& w, const float* __r
   const unsigned FULL = 0xffffffffu;
   const unsigned lt_mask = (1u << lane) - 1u;
   const int M = w.M;
-  const float target = fminf(1.25f * (float)k + 2.f, 0.5f * (float)(k + CS));
+  const float target = fminf(margin * (float)k + 2.f, 0.5f * (float)(k + CS));
   const float tiny = tau0 * 1e-6f;
-  const float grow = 1.25f + __fdividef(2.f, (float)k);
+  const float grow = margin + __fdividef(2.f, (float)k);
   float tau = tau0;
 
   for (u32 q = 0; q < w.qn; ++q) {
@@ -206,7 +209,7 @@ __device__ __forceinline__ void cell_queries(const CellWarp& w, const float* __r
 template <int E>  // E = CS / 32 survivor slots per lane
 __global__ void __launch_bounds__(KNN_WARPS * 32)
 knn_cell_kernel(GridView g, const float4* __restrict__ spts, const float* __restrict__ qb2, int k,
-                float tau0, u32* __restrict__ nbr, float* __restrict__ nd2, u64* __restrict__ kth,
+                float tau0, float margin, u32* __restrict__ nbr, float* __restrict__ nd2, u64* __restrict__ kth,
                 u32* __restrict__ fb_list, u32* __restrict__ fb_count) {
   constexpr int CS = 32 * E;
   constexpr int KNN_CAP = KNN_CAP_OF(E);
@@ -285,8 +288,8 @@ knn_cell_kernel(GridView g, const float4* __restrict__ spts, const float* __rest
   w.qs = qs;
   w.qn = qn;
   w.qoff = qoff;
-  if (R <= KNN_RR_SMALL(E)) cell_queries<E, KNN_RR_SMALL(E)>(w, qb2, k, tau0, nbr, nd2, kth, fb_list, fb_count, lane);
-  else cell_queries<E, KNN_RR_MAX(E)>(w, qb2, k, tau0, nbr, nd2, kth, fb_list, fb_count, lane);
+  if (R <= KNN_RR_SMALL(E)) cell_queries<E, KNN_RR_SMALL(E)>(w, qb2, k, tau0, margin, nbr, nd2, kth, fb_list, fb_count, lane);
+  else cell_queries<E, KNN_RR_MAX(E)>(w, qb2, k, tau0, margin, nbr, nd2, kth, fb_list, fb_count, lane);
 }
 
 template <int RL>
@@ -484,7 +487,9 @@ int knn_run(iftwt_ctx* c, int k) {
     auto kern = E == 1 ? knn_cell_kernel<1> : (E == 2 ? knn_cell_kernel<2> : knn_cell_kernel<4>);
     size_t sm = cell_kernel_smem(E);
     CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    LAUNCH(c, kern, blocks, KNN_WARPS * 32, sm, g, spts, (const float*)c->qb2.as<float>(), k, tau0,
+    const char* menv = getenv("IFTWT_KNN_MARGIN");
+    const float margin = menv ? (float)atof(menv) : 1.1f;  // swept on B200 (cfg3): 1.05 -> 5.76 ms, 1.12 -> 5.77, 1.25 -> 5.87, 1.4 -> 6.01
+    LAUNCH(c, kern, blocks, KNN_WARPS * 32, sm, g, spts, (const float*)c->qb2.as<float>(), k, tau0, margin,
            c->nbr.as<u32>(), c->nd2.as<float>(), c->kth.as<u64>(), c->fb_list.as<u32>(), fb_count);
   }
   cudaEventRecord(c->ev1[IFTWT_STAGE_KNN_CELL], c->stream);
