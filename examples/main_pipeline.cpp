@@ -2,16 +2,21 @@
 // include/iftwt_adapters.hpp.  Build:
 //   g++ -std=c++14 -Iinclude examples/main_pipeline.cpp -Liftwt_rg_b200/lib -liftwt
 //       -Wl,-rpath,$PWD/iftwt_rg_b200/lib -o main_pipeline
-// Input: a raw little-endian float32 file of {x,y,z,intensity} records, or a small built-in
+// Input: a .ply file (include/iftwt_io.hpp), a raw little-endian float32 file of {x,y,z,intensity} records, or a small built-in
 // scene when no file is given (the reference's ../cloud/lucy_gray.ply is absent from its tree).
 #include <cstdio>
 #include <cstdlib>
 #include <map>
 
 #include "iftwt_adapters.hpp"
+#include "iftwt_io.hpp"
 
 static global::CloudI::Ptr load_or_make(const char* path) {
   global::CloudI::Ptr cloud(new global::CloudI());
+  if (path && std::string(path).size() > 4 && std::string(path).substr(std::string(path).size() - 4) == ".ply") {
+    iftwt::io::loadPLYFile(path, *cloud);                                        // main.cpp:92
+    return cloud;
+  }
   if (path) {
     FILE* f = std::fopen(path, "rb");
     if (!f) return cloud;

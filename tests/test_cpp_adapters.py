@@ -39,3 +39,16 @@ def test_example_runs_the_reference_pipeline(tmp_path):
     assert m, out.stdout
     assert int(m.group(1)) == 60000 and 0 < int(m.group(2)) <= 60000
     assert int(m.group(4)) >= 1 and 1 <= int(m.group(5)) <= 10
+
+
+def test_ply_reader_writer(tmp_path):
+    """include/iftwt_io.hpp stands in for pcl::io::loadPLYFile / savePLYFile (main.cpp:81, 92, 128-129)."""
+    from iftwt_rg_b200 import api
+    api.load_library()
+    exe = str(tmp_path / "io_test")
+    libdir = os.path.join(ROOT, "iftwt_rg_b200", "lib")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "io_test.cpp"), "-L", libdir, "-liftwt",
+                           f"-Wl,-rpath,{libdir}", "-o", exe])
+    out = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "io ok" in out.stdout, out.stderr
