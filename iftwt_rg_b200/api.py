@@ -16,7 +16,7 @@ from . import _build
 
 IFTWT_MAX_COST = 500
 
-STAGES = ("upload", "grid", "knn", "graph", "normals", "seeds", "ift", "download", "knn_cell")
+STAGES = ("upload", "grid", "knn", "graph", "normals", "seeds", "ift", "download", "knn_cell", "graph_rg")
 
 
 class IftwtError(RuntimeError):
@@ -222,9 +222,11 @@ class Context:
         return cost, label
 
     def segment(self, k_graph: int, k_normals: int | None = None, rg: RgParams | None = None,
-                cost: np.ndarray | None = None, label: np.ndarray | None = None, download: bool = True):
+                cost: np.ndarray | None = None, label: np.ndarray | None = None, download: bool = True,
+                gradient_weights: bool = False):
         """main.cpp:97-123 in one call."""
-        p = SegmentParams(k_graph, k_normals or k_graph, rg or RgParams(number_of_neighbours=k_graph), 0)
+        p = SegmentParams(k_graph, k_normals or k_graph, rg or RgParams(number_of_neighbours=k_graph),
+                          1 if gradient_weights else 0)
         ns = C.c_size_t(0)
         if download:
             cost = np.empty(self.n, np.uint32) if cost is None else cost

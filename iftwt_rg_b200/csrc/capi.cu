@@ -101,6 +101,8 @@ void ctx_invalidate(iftwt_ctx* c) {
   c->graph_k = 0;
   c->graph_shares_nbr = false;
   c->mask_k = 0;
+  c->rdeg_k = 0;
+  c->rg_pre_valid = false;
   c->nrm_k = 0;
   c->seeds_valid = false;
   c->ift_valid = false;
@@ -378,20 +380,34 @@ int iftwt_segment(iftwt_ctx* c, const iftwt_segment_params* p, uint32_t* cost, u
   TRY(check_ctx(c));
   if (!p) return ctx_fail(c, IFTWT_ERR_INVALID, "null params");
   if (c->n == 0) return ctx_fail(c, IFTWT_ERR_STATE, "no cloud set");
-  if (p->weights != 0) return ctx_fail(c, IFTWT_ERR_UNSUPPORTED, "gradient weights are not built yet");
+  if (p->weights != 0 && p->weights != 1) return ctx_fail(c, IFTWT_ERR_INVALID, "weights must be 0 or 1");
   int kmax = p->k_graph;
   if (p->k_normals > kmax) kmax = p->k_normals;
   if (p->rg.number_of_neighbours > kmax) kmax = p->rg.number_of_neighbours;
   TRY(grid_build(c, kmax));
-  // graph first (its lists may be overwritten by the other neighbourhood sizes)
   TRY(knn_run(c, p->k_graph));
-  TRY(graph_build(c));
-  TRY(knn_run(c, p->k_normals));
-  TRY(normals_run(c));
-  TRY(seeds_run(c, &p->rg));
+  if (p->k_normals == p->k_graph && p->rg.number_of_neighbours == p->k_graph && p->rg.curvature_threshold >= 0.34f) {
+    // one neighbourhood size: graph mutuality and the region-growing arcs share one pass over the rows
+    TRY(normals_run(c));
+    TRY(fused_graph_rg_run(c, &p->rg));
+    TRY(graph_build(c));
+    TRY(seeds_run(c, &p->rg));
+  } else {
+    // graph first (its lists may be overwritten by the other neighbourhood sizes)
+    TRY(graph_build(c));
+    TRY(knn_run(c, p->k_normals));
+    TRY(normals_run(c));
+    TRY(seeds_run(c, &p->rg));
+  }
   if (n_seeds) *n_seeds = c->n_seeds;
-  TRY(ift_run(c, nullptr, c->seeds.as<u32>(), c->n_seeds));
   const size_t n = c->n;
+  const float* d_w = nullptr;
+  if (p->weights == 1) {  // morphological gradient of the intensity on the graph (graph.hpp:147-163)
+    ENSURE(c, c->out_b, n * 4);
+    TRY(morph_run(c, IFTWT_MORPH_GRADIENT, c->out_b.as<float>()));
+    d_w = c->out_b.as<float>();
+  }
+  TRY(ift_run(c, d_w, c->seeds.as<u32>(), c->n_seeds));
   {
     StageTimer st(c, IFTWT_STAGE_DOWNLOAD);
     if (cost) CU_TRY(c, cudaMemcpyAsync(cost, c->out_a.p, n * 4, cudaMemcpyDeviceToHost, c->stream));

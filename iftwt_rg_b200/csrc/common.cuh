@@ -77,6 +77,10 @@ struct iftwt_ctx {
   DevBuf g_fwd;                   // private copy of the forward rows once nbr is recomputed
   int mask_k = 0;                 // ow_mask describes the current k-NN lists when == knn_k
   DevBuf ow_mask;                 // u64 [n] bit j: arc u -> nbr[u][j] is one-way
+  int rdeg_k = 0;                 // g_deg holds reverse degrees + n_fwd of the current lists when == knn_k
+  bool rg_pre_valid = false;      // the fused pass left the region-growing union-find + arc list
+  int rg_pre_k = 0;
+  float rg_pre_cos = 0.f;
   // --- normals ---
   int nrm_k = 0;
   DevBuf nrm;  // float4 [n] sorted space {nx,ny,nz,curv}
@@ -162,6 +166,7 @@ void ctx_invalidate(iftwt_ctx* c);
 int graph_export(iftwt_ctx* c, u32* h_off, u32* h_adj, size_t cap, size_t* n_arcs);
 int normals_run(iftwt_ctx* c);                                             // normals.cu
 int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p);                     // seeds.cu
+int fused_graph_rg_run(iftwt_ctx* c, const iftwt_rg_params* p);
 int ift_run(iftwt_ctx* c, const float* d_w_orig /*or null*/, const u32* d_seeds_orig, size_t ns);  // ift.cu
 
 // ---- device helpers ----

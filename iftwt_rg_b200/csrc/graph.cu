@@ -110,7 +110,8 @@ int graph_build(iftwt_ctx* c) {
   StageTimer st(c, IFTWT_STAGE_GRAPH);
   const u32 n = (u32)c->n;
   const int k = c->knn_k;
-  TRY(knn_mutual_run(c, true));
+  if (!(c->mask_k == k && c->rdeg_k == k)) TRY(knn_mutual_run(c, true));  // else: left by the fused pass
+  c->rdeg_k = 0;  // g_deg becomes the fill cursor below
   ENSURE(c, c->g_off, ((size_t)n + 1) * 4);
   u32* rdeg = c->g_deg.as<u32>();
   u32* roff = c->g_off.as<u32>();

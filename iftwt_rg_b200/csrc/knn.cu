@@ -469,6 +469,8 @@ int knn_run(iftwt_ctx* c, int k) {
   if (c->knn_k == k) return IFTWT_OK;
   TRY(graph_detach_rows(c));  // the graph keeps its rows if they alias the lists we overwrite
   c->mask_k = 0;
+  c->rdeg_k = 0;
+  c->rg_pre_valid = false;
   StageTimer st(c, IFTWT_STAGE_KNN);
   const size_t n = c->n;
   ENSURE(c, c->nbr, n * k * 4);

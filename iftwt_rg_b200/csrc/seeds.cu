@@ -49,13 +49,16 @@ __device__ __forceinline__ bool smooth_pass(const float4 nu, const float4 nv, fl
 // keys in ORIGINAL order so that a stable 32-bit sort on the curvature bits breaks
 // ties by ascending original index: the canonical (curvature, index) order
 __global__ void rank_keys_kernel(const float4* __restrict__ nrm, const u32* __restrict__ inv, u32 n,
-                                 u32* __restrict__ keys, u32* __restrict__ vals, u32* __restrict__ parent) {
+                                 u32* __restrict__ keys, u32* __restrict__ vals) {
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   u32 j = inv[i];
   keys[i] = __float_as_uint(nrm[j].w);
   vals[i] = j;
-  parent[i] = i;
+}
+__global__ void iota_kernel(u32* __restrict__ a, u32 n) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = i;
 }
 __global__ void scatter_rank_kernel(const u32* __restrict__ sorted_vals, u32 n, u32* __restrict__ rank) {
   u32 r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -64,28 +67,50 @@ __global__ void scatter_rank_kernel(const u32* __restrict__ sorted_vals, u32 n, 
 }
 
 // One thread per vertex u (ECL-CC style): the smooth MUTUAL arcs to smaller ids are
-// hooked into the union-find with u's representative cached in a register; the smooth
-// ONE-WAY arcs are remembered in a bit mask and appended to (arc_u, arc_v) with one
-// global atomic per block.
+// hooked into the union-find with u's representative cached in a register (no two lanes of a
+// warp fight over the same root: a warp-per-vertex variant of this kernel spent 19 ms in CAS
+// retries); the smooth ONE-WAY arcs are remembered in a bit mask and appended to
+// (arc_u, arc_v) with one global atomic per block.
+// FUSED (iftwt_segment, one shared neighbourhood size): the same pass also decides mutuality
+// itself — one gather of the neighbour's k-th key per arc — and leaves ow_mask / rdeg / n_fwd
+// for graph_build, so the rows and the neighbours are visited once instead of twice.
+template <bool FUSED>
 __global__ void __launch_bounds__(256)
-rg_arcs_kernel(const u32* __restrict__ nbr, const u64* __restrict__ ow_mask, const float4* __restrict__ nrm,
-               u32 n, int k, float cos_thr, u32* __restrict__ parent, u32* __restrict__ counter,
-               u32* __restrict__ arc_u, u32* __restrict__ arc_v) {
-  __shared__ u32 s_warp[8];
+rg_arcs_kernel(const u32* __restrict__ nbr, const float* __restrict__ nd2, const u64* __restrict__ kth,
+               const float4* __restrict__ spts, u64* __restrict__ ow_mask, const float4* __restrict__ nrm, u32 n,
+               int k, float cos_thr, u32* __restrict__ parent, u32* __restrict__ counter, u32* __restrict__ arc_u,
+               u32* __restrict__ arc_v, u32* __restrict__ rdeg, unsigned long long* __restrict__ n_fwd) {
+  __shared__ u32 s_warp[8], s_fwd[8];
   __shared__ u32 s_base;
   const u32 u = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   u64 mask = 0;
+  u32 valid_cnt = 0;
   if (u < n) {
     const float4 nu = nrm[u];
-    const u64 ow = ow_mask[u];  // bit j: u is NOT among the k nearest of row[j] (graph.cu)
     const u32* row = nbr + (size_t)u * k;
+    u64 ow = 0;
+    u32 ou = 0;
+    if (FUSED) ou = __float_as_uint(spts[u].w);
+    else ow = ow_mask[u];  // bit j: u is NOT among the k nearest of row[j] (graph.cu)
     u32 ru = 0xFFFFFFFFu;
     for (int j = 0; j < k; ++j) {
-      u32 v = row[j];
+      const u32 v = row[j];
       if (v == SID_NONE || v == u) continue;
+      bool oneway;
+      if (FUSED) {
+        ++valid_cnt;
+        const u64 key = ((u64)__float_as_uint(nd2[(size_t)u * k + j]) << 32) | (u64)ou;
+        oneway = key > kth[v];
+        if (oneway) {
+          ow |= 1ull << j;
+          atomicAdd(&rdeg[v], 1u);
+        }
+      } else {
+        oneway = (ow >> j) & 1ull;
+      }
       if (!smooth_pass(nu, nrm[v], cos_thr)) continue;
-      if (!((ow >> j) & 1ull)) {
+      if (!oneway) {
         if (v < u) {  // the twin arc v->u is mutual and smooth too; one of the pair hooks
           if (ru == 0xFFFFFFFFu) ru = uf_find(parent, u);
           u32 rv = uf_find(parent, v);
@@ -108,6 +133,7 @@ rg_arcs_kernel(const u32* __restrict__ nbr, const u64* __restrict__ ow_mask, con
         mask |= 1ull << j;
       }
     }
+    if (FUSED) ow_mask[u] = ow;
   }
   // ---- block-aggregated append of the one-way arcs ----
   u32 cnt = (u32)__popcll(mask);
@@ -117,17 +143,24 @@ rg_arcs_kernel(const u32* __restrict__ nbr, const u64* __restrict__ ow_mask, con
     u32 t = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += t;
   }
+  if (FUSED) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) valid_cnt += __shfl_xor_sync(0xffffffffu, valid_cnt, o);
+  }
   if (lane == 31) s_warp[warp] = incl;
+  if (FUSED && lane == 0) s_fwd[warp] = valid_cnt;
   __syncthreads();
   if (threadIdx.x == 0) {
-    u32 tot = 0;
+    u32 tot = 0, fw = 0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
       u32 c = s_warp[w];
       s_warp[w] = tot;
       tot += c;
+      if (FUSED) fw += s_fwd[w];
     }
     s_base = tot ? atomicAdd(counter, tot) : 0u;
+    if (FUSED && fw) atomicAdd(n_fwd, (unsigned long long)fw);
   }
   __syncthreads();
   if (mask) {
@@ -258,6 +291,41 @@ __global__ void rg_seed_ids_kernel(const u32* __restrict__ sid_sorted, const u32
 
 }  // namespace
 
+// iftwt_segment fast path: graph mutuality + region-growing arcs in one pass.  Needs the k-NN
+// lists and the normals; leaves ow_mask / rdeg / n_fwd for graph_build and the union-find +
+// one-way arc list for seeds_run.
+int fused_graph_rg_run(iftwt_ctx* c, const iftwt_rg_params* p) {
+  if (c->knn_k == 0 || c->nrm_k != c->knn_k || p->number_of_neighbours != c->knn_k)
+    return ctx_fail(c, IFTWT_ERR_STATE, "fused graph/region-growing pass needs one shared neighbourhood size");
+  StageTimer st(c, IFTWT_STAGE_GRAPH_RG);
+  const u32 n = (u32)c->n;
+  const int k = c->knn_k;
+  const size_t ne = (size_t)n * k;
+  const float cos_thr = cosf(p->smoothness_threshold);
+  ENSURE(c, c->ow_mask, (size_t)n * 8);
+  ENSURE(c, c->g_deg, ((size_t)n + 1) * 4);
+  ENSURE(c, c->rg_parent, (size_t)n * 4);
+  ENSURE(c, c->rg_aux2, (ne + 1) * 8);
+  u32* sc = (u32*)c->scalars.as<int>();
+  u32* d_cnt = sc + 56;
+  unsigned long long* d_nfwd = (unsigned long long*)(c->scalars.as<int>() + 52);
+  CU_TRY(c, cudaMemsetAsync(d_cnt, 0, 16, c->stream));
+  CU_TRY(c, cudaMemsetAsync(d_nfwd, 0, 8, c->stream));
+  CU_TRY(c, cudaMemsetAsync(c->g_deg.p, 0, ((size_t)n + 1) * 4, c->stream));
+  u32* arc_u = c->rg_aux2.as<u32>();
+  LAUNCH(c, iota_kernel, div_up(n, 256), 256, 0, c->rg_parent.as<u32>(), n);
+  LAUNCH(c, rg_arcs_kernel<true>, div_up(n, 256), 256, 0, c->nbr.as<u32>(), c->nd2.as<float>(), c->kth.as<u64>(),
+         c->spts.as<float4>(), c->ow_mask.as<u64>(), c->nrm.as<float4>(), n, k, cos_thr, c->rg_parent.as<u32>(), d_cnt,
+         arc_u, arc_u + (ne + 1), c->g_deg.as<u32>(), d_nfwd);
+  CHECK_LAUNCH(c);
+  c->mask_k = k;
+  c->rdeg_k = k;
+  c->rg_pre_valid = true;
+  c->rg_pre_k = k;
+  c->rg_pre_cos = cos_thr;
+  return IFTWT_OK;
+}
+
 int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p) {
   if (c->nrm_k == 0) return ctx_fail(c, IFTWT_ERR_STATE, "normals are not computed (call iftwt_normals first)");
   if (p->number_of_neighbours != c->knn_k) {
@@ -301,7 +369,7 @@ int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p) {
     u32* k1 = c->keys_alt.as<u32>();
     u32* v0 = c->vals_alt.as<u32>();
     u32* v1 = seg_of;  // scratch
-    LAUNCH(c, rank_keys_kernel, div_up(n, 256), 256, 0, nrm, c->inv.as<u32>(), n, k0, v0, parent);
+    LAUNCH(c, rank_keys_kernel, div_up(n, 256), 256, 0, nrm, c->inv.as<u32>(), n, k0, v0);
     size_t tb = 0;
     CU_TRY(c, cub::DeviceRadixSort::SortPairs(nullptr, tb, k0, k1, v0, v1, (int)n, 0, 32, c->stream));
     ENSURE(c, c->tmp, tb);
@@ -310,16 +378,27 @@ int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p) {
     LAUNCH(c, scatter_rank_kernel, div_up(n, 256), 256, 0, v1, n, rank);
     CHECK_LAUNCH(c);
   }
-  // 2. mutual smooth arcs -> union-find; one-way smooth arcs -> list (worst-case capacity)
+  // 2. mutual smooth arcs -> union-find; one-way smooth arcs -> list (worst-case capacity).
+  //    Already done when iftwt_segment ran the fused graph + region-growing pass.
   u32* d_cnt = sc + 56;
-  CU_TRY(c, cudaMemsetAsync(d_cnt, 0, 16, c->stream));
-  ENSURE(c, c->rg_aux2, (ne + 1) * 8);
-  u32* arc_u = c->rg_aux2.as<u32>();
-  u32* arc_v = arc_u + (ne + 1);
-  if (c->mask_k != c->knn_k) TRY(knn_mutual_run(c, false));
-  LAUNCH(c, rg_arcs_kernel, div_up(n, 256), 256, 0, c->nbr.as<u32>(), c->ow_mask.as<u64>(), nrm, n, k, cos_thr,
-         parent, d_cnt, arc_u, arc_v);
-  CHECK_LAUNCH(c);
+  u32* arc_u = nullptr;
+  u32* arc_v = nullptr;
+  if (c->rg_pre_valid && c->rg_pre_k == k && c->rg_pre_cos == cos_thr) {
+    arc_u = c->rg_aux2.as<u32>();
+    arc_v = arc_u + (ne + 1);
+  } else {
+    CU_TRY(c, cudaMemsetAsync(d_cnt, 0, 16, c->stream));
+    ENSURE(c, c->rg_aux2, (ne + 1) * 8);
+    arc_u = c->rg_aux2.as<u32>();
+    arc_v = arc_u + (ne + 1);
+    LAUNCH(c, iota_kernel, div_up(n, 256), 256, 0, parent, n);
+    if (c->mask_k != c->knn_k) TRY(knn_mutual_run(c, false));
+    LAUNCH(c, rg_arcs_kernel<false>, div_up(n, 256), 256, 0, c->nbr.as<u32>(), (const float*)nullptr,
+           (const u64*)nullptr, (const float4*)nullptr, c->ow_mask.as<u64>(), nrm, n, k, cos_thr, parent, d_cnt, arc_u,
+           arc_v, (u32*)nullptr, (unsigned long long*)nullptr);
+    CHECK_LAUNCH(c);
+  }
+  c->rg_pre_valid = false;  // the union-find is consumed (flattened) below
   CU_TRY(c, cudaMemcpyAsync(hs + 56, d_cnt, 4, cudaMemcpyDeviceToHost, c->stream));
   // 3. component min rank, then label-min over one-way arcs
   CU_TRY(c, cudaMemsetAsync(L, 0xFF, (size_t)n * 4, c->stream));

@@ -85,7 +85,8 @@ enum {
   IFTWT_STAGE_IFT = 6,     /* watershed                                        */
   IFTWT_STAGE_DOWNLOAD = 7,
   IFTWT_STAGE_KNN_CELL = 8, /* the k-NN fast-path kernel alone (the roofline kernel)     */
-  IFTWT_STAGE_COUNT = 9
+  IFTWT_STAGE_GRAPH_RG = 9, /* iftwt_segment's fused graph-mutuality + region-growing arcs pass */
+  IFTWT_STAGE_COUNT = 10
 };
 
 typedef struct iftwt_stats {

@@ -266,3 +266,22 @@ def test_full_size_properties_1m(ctx):
     assert ns > 0
     seeds = np.unique(label[cost == 0])
     assert orc.ift_audit(off, adj, pts[:, 3], seeds.astype(np.int32), cost, label) == 0
+
+
+def test_segment_with_gradient_weights(ctx):
+    """iftwt_segment(weights = 1): the IFT runs on the morphological gradient of the intensity
+    over the graph (graph.hpp:147-163) instead of the raw vertex values."""
+    from iftwt_rg_b200 import api
+    pts = clouds()["primitives200k"]
+    k, theta = 16, 0.1
+    ctx.set_cloud(pts)
+    rg = api.RgParams(50, 10000, k, theta, 1.0)
+    cost, label, ns = ctx.segment(k, k, rg, gradient_weights=True)
+    ridx, _ = orc.knn_self(pts, k)
+    roff, radj = orc.knn_graph(ridx)
+    rn = orc.normals(pts, ridx)
+    rlab, _, kept, _ = orc.region_growing(rn, ridx, theta, 1.0, 50, 10000)
+    rseeds, _ = orc.rg_seeds(pts, rlab, kept)
+    grad = orc.morph(roff, radj, pts[:, 3], orc.MORPH_GRADIENT)
+    rcost, rlabel = orc.ift(roff, radj, grad, rseeds, orc.POLICY_C)
+    assert ns == kept and np.array_equal(cost, rcost) and np.array_equal(label, rlabel)
