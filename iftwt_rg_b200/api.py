@@ -98,6 +98,8 @@ def load_library(build_if_missing: bool = True):
     lib.iftwt_knn_device.argtypes = [vp, i32, vp, vp]
     lib.iftwt_normals_device.argtypes = [vp, i32, vp]
     lib.iftwt_set_knn_rows_device.argtypes = [vp, i32, vp, vp]
+    lib.iftwt_morph_rgb.argtypes = [vp, i32, vp]
+    lib.iftwt_rgb_to_gray.argtypes = [vp, i32, C.POINTER(C.c_double)]
     lib.iftwt_stage_ms.argtypes = [vp, i32, C.POINTER(f32)]
     lib.iftwt_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.iftwt_reset_counters.argtypes = [vp]
@@ -279,6 +281,17 @@ class Context:
         if ns.value:
             self._check(self._lib.iftwt_regmin_seeds(self._h, _ptr(seeds), ns.value, C.byref(ns)))
         return seeds
+
+    # -- colour path (graco.hpp, main.cpp:16-89) ---------------------------------
+    def morph_rgb(self, op: int) -> np.ndarray:
+        out = np.empty(self.n, np.uint32)
+        self._check(self._lib.iftwt_morph_rgb(self._h, op, _ptr(out)))
+        return out
+
+    def rgb_to_gray(self, otsu: bool = False) -> float:
+        t = C.c_double(0)
+        self._check(self._lib.iftwt_rgb_to_gray(self._h, 1 if otsu else 0, C.byref(t)))
+        return float(t.value)
 
     # -- device-pointer variants (multi-GPU plumbing) --------------------------
     def knn_device(self, k: int, d_idx: int, d_d2: int = 0):

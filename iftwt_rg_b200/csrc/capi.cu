@@ -591,6 +591,23 @@ int iftwt_set_knn_rows_device(iftwt_ctx* c, int k, const int32_t* d_idx, const f
   return IFTWT_OK;
 }
 
+int iftwt_morph_rgb(iftwt_ctx* c, int op, uint32_t* rgb_out) {
+  TRY(check_ctx(c));
+  if (!rgb_out) return ctx_fail(c, IFTWT_ERR_INVALID, "null out");
+  ENSURE(c, c->out_a, c->n * 4);
+  TRY(morph_rgb_run(c, op, c->out_a.as<u32>()));
+  CU_TRY(c, cudaMemcpyAsync(rgb_out, c->out_a.p, c->n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return IFTWT_OK;
+}
+
+int iftwt_rgb_to_gray(iftwt_ctx* c, int otsu, double* threshold) {
+  TRY(check_ctx(c));
+  TRY(rgb_to_gray_run(c, otsu, threshold));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return IFTWT_OK;
+}
+
 int iftwt_stage_ms(iftwt_ctx* c, int stage, float* ms) {
   TRY(check_ctx(c));
   if (stage < 0 || stage >= IFTWT_STAGE_COUNT || !ms) return ctx_fail(c, IFTWT_ERR_INVALID, "bad stage");

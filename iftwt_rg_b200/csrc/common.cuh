@@ -159,6 +159,8 @@ int cloud_resolution_run(iftwt_ctx* c, double overlap, double* res);            
 int voxel_graph_run(iftwt_ctx* c, double resolution, int k_hint);
 int morph_run(iftwt_ctx* c, int op, float* d_out_orig);
 int regmin_run(iftwt_ctx* c);
+int morph_rgb_run(iftwt_ctx* c, int op, u32* d_out_orig);
+int rgb_to_gray_run(iftwt_ctx* c, int otsu, double* threshold);
 int region_adjacency_run(iftwt_ctx* c);                                     // hierarchy.cu
 int region_info_run(iftwt_ctx* c);
 int cluster_run(iftwt_ctx* c, int num_regions, u32* d_cluster_orig, size_t* n_clusters);

@@ -196,6 +196,63 @@ __global__ void regmin_kernel(GraphView g, const float4* __restrict__ pts_in, co
   flag_orig[perm[s]] = is_min ? 1 : 0;
 }
 
+
+// ---- colour path: GraCo::morph_c_base (graco.hpp:301-351) and the grey / Otsu prep (main.cpp:16-76) ----
+// The cloud's 4th channel carries PCL's packed rgb float (bits 0xAARRGGBB); it is only ever
+// moved, never computed on.  Among equal r+g+b the reference keeps the first neighbour in
+// (address) iteration order; the canonical choice is the smallest ORIGINAL vertex id, which
+// makes the result the order-free min / max of the key (sum, id).
+__device__ __forceinline__ int rgb_sum(u32 c) { return (int)((c >> 16) & 255) + (int)((c >> 8) & 255) + (int)(c & 255); }
+__global__ void morph_rgb_kernel(GraphView g, const float4* __restrict__ pts_in, const u32* __restrict__ perm, u32 n,
+                                 int op, u32* __restrict__ out_orig) {
+  u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const bool erode = op == 4;
+  u32 best = erode ? 0x00FFFFFFu : 0u;
+  int best_sum = rgb_sum(best);
+  u32 best_id = 0xFFFFFFFFu;
+  auto visit = [&](u32 u) {
+    const u32 o = perm[u];
+    const u32 c = __float_as_uint(pts_in[o].w) & 0x00FFFFFFu;
+    const int sm = rgb_sum(c);
+    // strict improvement over the initial white / black; among real candidates (sum, id) order
+    const bool better = erode ? (sm < best_sum || (sm == best_sum && best_id != 0xFFFFFFFFu && o < best_id))
+                              : (sm > best_sum || (sm == best_sum && best_id != 0xFFFFFFFFu && o < best_id));
+    if (better) {
+      best = c;
+      best_sum = sm;
+      best_id = o;
+    }
+  };
+  visit(s);
+  for_each_neighbour(g, s, visit);
+  out_orig[perm[s]] = best;
+}
+// cv::cvtColor(CV_RGB2GRAY), 8-bit fixed point [OpenCV-recall]; also the 256-bin histogram
+__global__ void rgb_gray_kernel(const float4* __restrict__ pts_in, u32 n, unsigned char* __restrict__ gray,
+                                unsigned long long* __restrict__ hist) {
+  __shared__ u32 sh[256];
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const u32 c = __float_as_uint(pts_in[i].w);
+    const u32 r = (c >> 16) & 255, gg = (c >> 8) & 255, b = c & 255;
+    const u32 v = (r * 4899u + gg * 9617u + b * 1868u + 8192u) >> 14;
+    gray[i] = (unsigned char)v;
+    atomicAdd(&sh[v], 1u);
+  }
+  __syncthreads();
+  if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+__global__ void gray_store_kernel(const unsigned char* __restrict__ gray, u32 n, int otsu, float thr,
+                                  float4* __restrict__ pts_in) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = (float)gray[i];
+  if (otsu) v = v < thr ? 0.f : 255.f;  // main.cpp:48-51
+  pts_in[i].w = v;
+}
+
 GraphView graph_view(iftwt_ctx* c) {
   GraphView g;
   g.fwd = c->graph_shares_nbr ? c->nbr.as<u32>() : c->g_fwd.as<u32>();
@@ -326,6 +383,63 @@ int voxel_graph_run(iftwt_ctx* c, double resolution, int k_hint) {
   c->graph_kind = 2;
   c->graph_shares_nbr = false;
   c->stats.n_arcs = c->n_arcs;
+  return IFTWT_OK;
+}
+
+
+int morph_rgb_run(iftwt_ctx* c, int op, u32* d_out_orig) {
+  if (c->graph_k == 0) return ctx_fail(c, IFTWT_ERR_STATE, "graph is not built");
+  if (op != 3 && op != 4) return ctx_fail(c, IFTWT_ERR_INVALID, "colour morphology has dilate (3) and erode (4) only");
+  const u32 n = (u32)c->n;
+  LAUNCH(c, morph_rgb_kernel, div_up(n, 128), 128, 0, graph_view(c), c->pts_in.as<float4>(), c->perm.as<u32>(), n, op,
+         d_out_orig);
+  CHECK_LAUNCH(c);
+  return IFTWT_OK;
+}
+
+// packed rgb -> grey (optionally binarised at the Otsu threshold) in the cloud's 4th channel
+int rgb_to_gray_run(iftwt_ctx* c, int otsu, double* threshold) {
+  if (c->n == 0) return ctx_fail(c, IFTWT_ERR_STATE, "no cloud set");
+  const u32 n = (u32)c->n;
+  ENSURE(c, c->scalars, 4096);
+  ENSURE(c, c->out_b, (size_t)n + 256 * 8 + 16);
+  unsigned char* gray = c->out_b.as<unsigned char>() + 256 * 8;
+  unsigned long long* hist = c->out_b.as<unsigned long long>();
+  CU_TRY(c, cudaMemsetAsync(hist, 0, 256 * 8, c->stream));
+  LAUNCH(c, rgb_gray_kernel, c->sm_count * 4, 256, 0, c->pts_in.as<float4>(), n, gray, hist);
+  CHECK_LAUNCH(c);
+  double thr = -1.0;
+  if (otsu) {
+    unsigned long long h[256];
+    CU_TRY(c, cudaMemcpyAsync(h, hist, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    // getThreshVal_Otsu_8u [OpenCV-recall, 3.2]
+    double mu = 0, scale = 1. / (double)n;
+    for (int i = 0; i < 256; ++i) mu += i * (double)h[i];
+    mu *= scale;
+    double mu1 = 0, q1 = 0, max_sigma = 0, max_val = 0;
+    for (int i = 0; i < 256; ++i) {
+      double p_i = h[i] * scale;
+      mu1 *= q1;
+      q1 += p_i;
+      double q2 = 1. - q1;
+      if (fmin(q1, q2) < FLT_EPSILON || fmax(q1, q2) > 1. - FLT_EPSILON) continue;
+      mu1 = (mu1 + i * p_i) / q1;
+      double mu2 = (mu - q1 * mu1) / q2;
+      double sigma = q1 * q2 * (mu1 - mu2) * (mu1 - mu2);
+      if (sigma > max_sigma) {
+        max_sigma = sigma;
+        max_val = i;
+      }
+    }
+    thr = max_val;
+  }
+  LAUNCH(c, gray_store_kernel, div_up(n, 256), 256, 0, gray, n, otsu, (float)thr, c->pts_in.as<float4>());
+  CHECK_LAUNCH(c);
+  if (threshold) *threshold = thr;
+  // the values every later stage reads have changed; the geometry (grid, k-NN, graph) has not
+  c->ift_valid = false;
+  c->rag_valid = false;
   return IFTWT_OK;
 }
 

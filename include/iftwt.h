@@ -244,6 +244,18 @@ IFTWT_API int iftwt_normals_device(iftwt_ctx* ctx, int k, float* d_out4);
  * single-GPU graph / seeds / IFT stages.  The cloud must be set. */
 IFTWT_API int iftwt_set_knn_rows_device(iftwt_ctx* ctx, int k, const int32_t* d_idx, const float* d_d2);
 
+/* ---- colour path (graco.hpp, main.cpp:16-89): the cloud's 4th channel carries PCL's packed
+ * rgb float (pcl::PointXYZRGB: iftwt_set_cloud(points, 32, n, 0, 16)) -------------------- */
+
+/* GraCo::morph_erode / morph_dilate (graco.hpp:301-351) on the current graph: per vertex the
+ * colour (0x00RRGGBB) of the closed-neighbourhood vertex with the smallest (erode, op 4) or
+ * largest (dilate, op 3) r+g+b; ties go to the smallest vertex id. */
+IFTWT_API int iftwt_morph_rgb(iftwt_ctx* ctx, int op, uint32_t* rgb_out);
+/* cloudGray / cloudRGB2GRAY (main.cpp:16-76): replace the packed colour by its 8-bit grey
+ * (cv::cvtColor RGB2GRAY); with otsu != 0 binarise at the Otsu threshold (main.cpp:44-51),
+ * returned in *threshold.  The cloud becomes an XYZI cloud for the stages that follow. */
+IFTWT_API int iftwt_rgb_to_gray(iftwt_ctx* ctx, int otsu, double* threshold);
+
 /* Instrumentation (the reference's is one std::time pair, ift.hpp:172-173). */
 IFTWT_API int iftwt_stage_ms(iftwt_ctx* ctx, int stage, float* ms); /* CUDA-event time of the last run of a stage */
 IFTWT_API int iftwt_get_stats(iftwt_ctx* ctx, iftwt_stats* out);

@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
+#include <cstring>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -224,6 +225,108 @@ class Graph {
   std::size_t n_ = 0;
   double voxel_size_ = 0;
 };
+
+enum class MORPH_COLOR : char { dilate = 3, erode = 4 };  // graco.hpp:36
+
+// graco.hpp:38-352 — the RGB twin of Graph; what the reference's live main() runs
+// (GraCo gc(cloud_t, 5.0); gc.morph_erode(cloud_g), main.cpp:87-89).  The packed colour word
+// of pcl::PointXYZRGB travels in the ctx's 4th channel untouched.
+class GraCo {
+ public:
+  explicit GraCo(global::CloudT::Ptr cloud, double ovrlp = 1.01, int device = 0)
+      : s_(std::make_shared<iftwt::Session>(device)) {
+    static_assert(sizeof(global::PointT) == 32, "PointXYZRGB layout");
+    n_ = cloud->points.size();
+    s_->check(iftwt_set_cloud(s_->get(), cloud->points.data(), sizeof(global::PointT), n_, 0, 16));
+    double voxel = 0;
+    s_->check(iftwt_cloud_resolution(s_->get(), ovrlp, &voxel));
+    voxel_size_ = voxel;
+    s_->check(iftwt_voxel_graph(s_->get(), voxel, &n_));
+  }
+  global::CloudT::Ptr getCloud() { return cloud_with(nullptr); }  // graco.hpp:137-140
+  global::CloudT::Ptr morph_erode(global::CloudT::Ptr out) { return morph(IFTWT_MORPH_ERODE, out); }
+  global::CloudT::Ptr morph_dilate(global::CloudT::Ptr out) { return morph(IFTWT_MORPH_DILATE, out); }
+  iftwt::CsrGraph getAdjacencyList() {
+    iftwt::CsrGraph g;
+    std::size_t arcs = 0;
+    s_->check(iftwt_graph_csr(s_->get(), nullptr, nullptr, 0, &arcs));
+    g.off.resize(n_ + 1);
+    g.adj.resize(arcs);
+    s_->check(iftwt_graph_csr(s_->get(), g.off.data(), g.adj.data(), arcs, &arcs));
+    return g;
+  }
+  std::size_t size() const { return n_; }
+  double voxelSize() const { return voxel_size_; }
+  const std::shared_ptr<iftwt::Session>& session() const { return s_; }
+
+ private:
+  global::CloudT::Ptr cloud_with(const std::vector<std::uint32_t>* rgb) {
+    std::vector<float> buf(4 * n_);
+    std::size_t n = 0;
+    s_->check(iftwt_get_cloud(s_->get(), buf.data(), n_, &n));
+    global::CloudT::Ptr out(new global::CloudT());
+    out->points.resize(n);
+    for (std::size_t i = 0; i < n; ++i) {
+      global::PointT& p = out->points[i];
+      p.x = buf[4 * i];
+      p.y = buf[4 * i + 1];
+      p.z = buf[4 * i + 2];
+      std::uint32_t w;
+      if (rgb) w = (*rgb)[i];
+      else std::memcpy(&w, &buf[4 * i + 3], 4);
+      p.r = (std::uint8_t)(w >> 16);
+      p.g = (std::uint8_t)(w >> 8);
+      p.b = (std::uint8_t)w;
+    }
+    out->width = (std::uint32_t)n;
+    out->height = 1;
+    return out;
+  }
+  global::CloudT::Ptr morph(int op, global::CloudT::Ptr out) {
+    std::vector<std::uint32_t> rgb(n_);
+    s_->check(iftwt_morph_rgb(s_->get(), op, rgb.data()));
+    global::CloudT::Ptr c = cloud_with(&rgb);
+    if (out) {
+      out->points.swap(c->points);
+      out->width = (std::uint32_t)out->points.size();
+      out->height = 1;
+      return out;
+    }
+    return c;
+  }
+  std::shared_ptr<iftwt::Session> s_;
+  std::size_t n_ = 0;
+  double voxel_size_ = 0;
+};
+
+// main.cpp:16-76: cloudGray (otsu = false) and cloudRGB2GRAY (otsu = true).  The conversion runs
+// on the device of a scratch ctx; the XYZI cloud it returns feeds Graph(cloud_i) (main.cpp:97).
+inline global::CloudI::Ptr cloudGray(global::CloudT::Ptr cloud, bool otsu = false, double* threshold = nullptr,
+                                     int device = 0) {
+  iftwt::Session s(device);
+  const std::size_t n = cloud->points.size();
+  s.check(iftwt_set_cloud(s.get(), cloud->points.data(), sizeof(global::PointT), n, 0, 16));
+  double t = -1;
+  s.check(iftwt_rgb_to_gray(s.get(), otsu ? 1 : 0, &t));
+  if (threshold) *threshold = t;
+  std::vector<float> buf(4 * n);
+  std::size_t m = 0;
+  s.check(iftwt_get_cloud(s.get(), buf.data(), n, &m));
+  global::CloudI::Ptr out(new global::CloudI());
+  out->points.resize(m);
+  for (std::size_t i = 0; i < m; ++i) {
+    out->points[i].x = buf[4 * i];
+    out->points[i].y = buf[4 * i + 1];
+    out->points[i].z = buf[4 * i + 2];
+    out->points[i].intensity = buf[4 * i + 3];
+  }
+  out->width = cloud->width;
+  out->height = cloud->height;
+  return out;
+}
+inline global::CloudI::Ptr cloudRGB2GRAY(global::CloudT::Ptr cloud, double* threshold = nullptr, int device = 0) {
+  return cloudGray(cloud, true, threshold, device);
+}
 
 namespace iftwt {
 // pcl::NormalEstimationOMP<PointI, Normal> as used at main.cpp:104-109, on the graph's cloud

@@ -1306,3 +1306,77 @@ ORC_API i64 orc_cluster_literal(i64 n, const u32* label, const u32* mst_a, const
   }
   return (i64)regions.size();
 }
+
+// =============================================================================
+// Colour path: GraCo colour morphology and the grey / Otsu prep
+// =============================================================================
+// GraCo::morph_c_base (graco.hpp:301-351): over the closed neighbourhood, erode takes the
+// colour of the neighbour with the smallest r+g+b (starting from white), dilate the largest
+// (starting from black); the update is strict, so among equal sums the first neighbour in
+// iteration order wins — ascending vertex id here, the canonical stand-in for address order.
+// rgb words are 0x00RRGGBB (the alpha byte is ignored and cleared).  op: 3 dilate, 4 erode.
+ORC_API void orc_morph_rgb(const u32* off, const u32* adj, i64 n, const u32* rgb, int op, u32* out) {
+  auto sum = [](u32 c) { return (int)((c >> 16) & 255) + (int)((c >> 8) & 255) + (int)(c & 255); };
+#pragma omp parallel for schedule(static)
+  for (i64 v = 0; v < n; ++v) {
+    u32 best = op == 4 ? 0x00FFFFFFu : 0u;
+    // closed neighbourhood in ascending id: neighbours below v, v itself, neighbours above v
+    bool self_done = false;
+    auto visit = [&](u32 u) {
+      u32 c = rgb[u] & 0x00FFFFFFu;
+      if (op == 4 ? sum(c) < sum(best) : sum(c) > sum(best)) best = c;
+    };
+    for (u32 e = off[v]; e < off[v + 1]; ++e) {
+      if (!self_done && adj[e] > (u32)v) {
+        visit((u32)v);
+        self_done = true;
+      }
+      visit(adj[e]);
+    }
+    if (!self_done) visit((u32)v);
+    out[v] = best;
+  }
+}
+
+// cloudGray / cloudRGB2GRAY (main.cpp:16-76) [OpenCV-recall, 3.2]: per point
+// cv::cvtColor(CV_RGB2GRAY) on 8-bit data = (r*4899 + g*9617 + b*1868 + 8192) >> 14; with
+// otsu != 0 the grey values are binarised at cv::threshold(..., CV_THRESH_OTSU)'s threshold
+// (getThreshVal_Otsu_8u): v < t -> 0 else 255 (main.cpp:48-51).  Returns the threshold (or -1).
+ORC_API double orc_rgb_to_gray(const u32* rgb, i64 n, int otsu, float* gray) {
+  std::vector<unsigned char> g((size_t)n);
+  for (i64 i = 0; i < n; ++i) {
+    unsigned r = (rgb[i] >> 16) & 255, gg = (rgb[i] >> 8) & 255, b = rgb[i] & 255;
+    g[i] = (unsigned char)((r * 4899u + gg * 9617u + b * 1868u + 8192u) >> 14);
+  }
+  double thr = -1.0;
+  if (otsu) {
+    const int N = 256;
+    i64 h[N] = {0};
+    for (i64 i = 0; i < n; ++i) h[g[i]]++;
+    double mu = 0, scale = 1. / (double)n;
+    for (int i = 0; i < N; ++i) mu += i * (double)h[i];
+    mu *= scale;
+    double mu1 = 0, q1 = 0, max_sigma = 0, max_val = 0;
+    for (int i = 0; i < N; ++i) {
+      double p_i = h[i] * scale;
+      mu1 *= q1;
+      q1 += p_i;
+      double q2 = 1. - q1;
+      if (std::min(q1, q2) < FLT_EPSILON || std::max(q1, q2) > 1. - FLT_EPSILON) continue;
+      mu1 = (mu1 + i * p_i) / q1;
+      double mu2 = (mu - q1 * mu1) / q2;
+      double sigma = q1 * q2 * (mu1 - mu2) * (mu1 - mu2);
+      if (sigma > max_sigma) {
+        max_sigma = sigma;
+        max_val = i;
+      }
+    }
+    thr = max_val;
+  }
+  for (i64 i = 0; i < n; ++i) {
+    float v = (float)g[i];
+    if (otsu) v = v < thr ? 0.f : 255.f;
+    gray[i] = v;
+  }
+  return thr;
+}

@@ -271,3 +271,21 @@ def cluster_literal(label, mst_a, mst_b, mst_w, num_regions):
     k = int(f(C.c_int64(len(label)), _p(label), _p(mst_a), _p(mst_b), _p(mst_w), C.c_int64(len(mst_a)),
               C.c_int(num_regions), _p(out)))
     return out, k
+
+
+def morph_rgb(off, adj, rgb, op):
+    off = np.ascontiguousarray(off, np.uint32)
+    adj = np.ascontiguousarray(adj, np.uint32)
+    rgb = np.ascontiguousarray(rgb, np.uint32)
+    out = np.empty_like(rgb)
+    lib().orc_morph_rgb(_p(off), _p(adj), C.c_int64(len(rgb)), _p(rgb), C.c_int(op), _p(out))
+    return out
+
+
+def rgb_to_gray(rgb, otsu=False):
+    rgb = np.ascontiguousarray(rgb, np.uint32)
+    gray = np.empty(len(rgb), np.float32)
+    f = lib().orc_rgb_to_gray
+    f.restype = C.c_double
+    thr = float(f(_p(rgb), C.c_int64(len(rgb)), C.c_int(1 if otsu else 0), _p(gray)))
+    return gray, thr

@@ -52,3 +52,25 @@ def test_ply_reader_writer(tmp_path):
                            f"-Wl,-rpath,{libdir}", "-o", exe])
     out = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=60)
     assert out.returncode == 0 and "io ok" in out.stdout, out.stderr
+
+
+def _build_cpp(tmp_path, name):
+    from iftwt_rg_b200 import api
+    api.load_library()
+    exe = str(tmp_path / name)
+    libdir = os.path.join(ROOT, "iftwt_rg_b200", "lib")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", name + ".cpp"), "-L", libdir, "-liftwt",
+                           f"-Wl,-rpath,{libdir}", "-o", exe])
+    return exe
+
+
+def test_graco_adapter_compiles(tmp_path):
+    assert os.path.exists(_build_cpp(tmp_path, "graco_test"))
+
+
+@pytest.mark.gpu
+def test_graco_adapter_runs_the_live_main(tmp_path):
+    """main.cpp:80-89 (GraCo gc(cloud_t, 5.0); gc.morph_erode) and the Otsu prep through the adapters."""
+    out = subprocess.run([_build_cpp(tmp_path, "graco_test")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "graco ok" in out.stdout, out.stdout + out.stderr
