@@ -90,8 +90,8 @@ struct iftwt_ctx {
   size_t n_seeds = 0;
   bool seeds_valid = false;
   // --- ift ---
-  DevBuf ift_state, ift_parent, ift_w, ift_byw, ift_local;
-  DevBuf ift_info; // u64 [n] FINAL | weight << 32 | label: one gather per arc visit
+  DevBuf ift_w, ift_byw;
+  DevBuf ift_node; // u64 [n] union-find link | result | weight in one word (ift.cu)
   DevBuf ift_res;  // u64 [n] resolved (cost << 32 | label) per sorted vertex
   DevBuf ift_wf;   // float [n] the weights the IFT ran on, sorted space
   // --- hierarchy ---

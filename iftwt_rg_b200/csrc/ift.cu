@@ -17,12 +17,14 @@
 // vertex of such a component gets cost c, and under the min-seed tie policy
 // (DESIGN.md policy C: a vertex keeps the smallest (cost, seed id) offered by a
 // final neighbour) the whole component takes the smallest seed label on its rim.
-// So each level is one incremental union-find step over the vertices whose weight
-// IS c (each vertex and each arc is touched once over the whole run):
-//   A. every newly opened vertex t (w[t] == c) unions with its open, unconquered
-//      neighbours and remembers the smallest label among its conquered neighbours;
-//   B. that label is pushed to the component root with one atomicMin on the packed
-//      (cost << 32 | label) word — the root's word is the whole component's result.
+// So each level is ONE launch of an incremental union-find step over the vertices whose
+// weight IS c (each vertex and each arc is touched once over the whole run): every newly
+// opened vertex t (w[t] == c) unions with its open, not yet conquered neighbours, takes the
+// smallest label among its neighbours conquered at earlier levels, and offers (c, label) to
+// its component's root with one atomicMin.  Unions and offers of the same level interleave
+// freely: the link, the result and the weight of a vertex share one 64-bit word (see node[]
+// below), so a hook (atomicCAS) and an offer (atomicMin) on the same root are ordered by the
+// hardware and a result is never stranded on a root that has just been hooked.
 // Lakes (open components no conquered vertex touches yet) simply stay in the
 // union-find until a later level reaches them.  Levels stay strictly ordered, which
 // is what makes the labels schedule independent (SURVEY finding 6); inside a level
@@ -35,31 +37,51 @@
 
 #define W_CLOSED 511u  // weight >= MAX_COST: the vertex can never be conquered
 #define LBL_NONE 0xFFFFFFFFu
-// info[v] = FINAL | weight << 32 | label: everything a neighbour needs from v in ONE 8-byte
-// gather.  FINAL is set (with the component's label) once v's component is conquered — by the
-// finalize blocks that ride along with the next level's launch, or lazily by the first
-// visitor that resolves v through the union-find.  A conquered component never changes, so
-// every writer stores the same word.
-#define INFO_FINAL 0x8000000000000000ull
-#define INFO_W(e) ((u32)((e) >> 32) & 0x1FFu)
+// node[v] — ONE 8-byte word per vertex carries the union-find link, the component's result and
+// the vertex weight, so that an arc visit is one gather and every update is one atomic on the
+// word it concerns (no fences, no second array to keep in step):
+//   hi == 0                  PARENT     lo = parent vertex; v is hooked for good
+//   hi == 1                  SEED       cost 0, lo = label (= the seed's original index)
+//   hi == c + 2, c < 500     CONQUERED  at level c with label lo.  While level c is running the
+//                                       word is "in flight": later offers may still lower lo
+//   hi == 502 + w            OPEN/CLOSED root that no offer has reached; w = its own weight
+// PARENT < every result word < every unconquered word, so atomicMin(word, offer) is a no-op
+// on a hooked vertex (and returns the link to follow), lowers an in-flight result, and
+// conquers an unconquered root.  A hook is atomicCAS(root word -> PARENT): it succeeds only on
+// the exact word it read, so whatever result had landed on the hooked root is known to the
+// hooking thread, which forwards it to the new root.  Words of components conquered at an
+// earlier level never change again; any thread may copy such a root word over a member's
+// PARENT word ("lazy finalize") to cut later chases short.
+#define NODE_HI(x) ((u32)((x) >> 32))
+#define NODE_LO(x) ((u32)(x))
+#define NODE_UNCONQ 502u
 
 namespace {
 
-__device__ __forceinline__ u32 uf_find(u32* parent, u32 v) {
-  u32 p = parent[v];
-  while (p != v) {
-    u32 gp = parent[p];
-    if (gp != p) parent[v] = gp;
+// follows PARENT links from v; returns the first non-PARENT word, v = its vertex (path halving)
+__device__ __forceinline__ u64 node_find(u64* __restrict__ node, u32& v, u64 x) {
+  while (NODE_HI(x) == 0) {
+    const u32 p = NODE_LO(x);
+    const u64 y = node[p];
+    if (NODE_HI(y) == 0) node[v] = y;
     v = p;
-    p = gp;
+    x = y;
   }
-  return v;
+  return x;
+}
+// an offer travels up the links until it lands on a root word
+__device__ __forceinline__ void node_offer(u64* __restrict__ node, u32 v, u64 val) {
+  while (true) {
+    const u64 old = atomicMin((unsigned long long*)&node[v], (unsigned long long)val);
+    if (NODE_HI(old) != 0) return;
+    v = NODE_LO(old);
+  }
 }
 // weights (original order) -> u16 per sorted vertex; flags non-integer / negative input
 __global__ void ift_init_kernel(const float* __restrict__ w_orig, const float4* __restrict__ pts_in,
                                 const u32* __restrict__ perm, u32 n, unsigned short* __restrict__ w16,
-                                u64* __restrict__ state, u32* __restrict__ parent, u32* __restrict__ ids,
-                                float* __restrict__ wf, u64* __restrict__ info, u32* __restrict__ bad) {
+                                u64* __restrict__ node, u32* __restrict__ ids, float* __restrict__ wf,
+                                u32* __restrict__ bad) {
   u32 v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n) return;
   u32 o = perm[v];
@@ -73,14 +95,11 @@ __global__ void ift_init_kernel(const float* __restrict__ w_orig, const float4* 
     q = w >= (float)IFTWT_MAX_COST ? (unsigned short)W_CLOSED : (unsigned short)w;
   }
   w16[v] = q;
-  info[v] = ((u64)q << 32) | (u64)LBL_NONE;
-  state[v] = ((u64)IFTWT_MAX_COST << 32) | (u64)o;
-  parent[v] = v;
+  node[v] = (u64)(NODE_UNCONQ + q) << 32;
   ids[v] = v;
 }
 __global__ void ift_seed_kernel(const u32* __restrict__ seeds_orig, u32 ns, const u32* __restrict__ inv, u32 n,
-                                unsigned short* __restrict__ w16, u64* __restrict__ state,
-                                u64* __restrict__ info, u32* __restrict__ bad) {
+                                unsigned short* __restrict__ w16, u64* __restrict__ node, u32* __restrict__ bad) {
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ns) return;
   u32 o = seeds_orig[i];
@@ -89,9 +108,8 @@ __global__ void ift_seed_kernel(const u32* __restrict__ seeds_orig, u32 ns, cons
     return;
   }
   u32 v = inv[o];
-  w16[v] = 0;            // open from level 0 on; its own value never matters (ift.hpp:138)
-  state[v] = (u64)o;     // cost 0, label = itself
-  info[v] = INFO_FINAL | (u64)o;
+  w16[v] = 0;                      // listed with level 0; its own value never matters (ift.hpp:138)
+  node[v] = (1ull << 32) | (u64)o; // cost 0, label = itself, conquered before level 0 starts
 }
 // seg_off[c] = first position in the weight-sorted vertex list with weight >= c, c = 0..512
 __global__ void ift_segments_kernel(const unsigned short* __restrict__ w_sorted, u32 n, u32* __restrict__ seg_off) {
@@ -106,118 +124,113 @@ __global__ void ift_segments_kernel(const unsigned short* __restrict__ w_sorted,
   seg_off[c] = lo;
 }
 
-// A: one warp per newly opened vertex.  adjacency(t) = its k-NN row + its reverse arcs.
-struct OpenCtx {
-  u64* info;
-  const u64* state;
-  u32* parent;
-  u32 level;
-};
-// rt = this lane's belief of t's representative (t itself until a hook says otherwise); a stale
-// belief only costs a failed CAS, which returns the way up.
-__device__ __forceinline__ void ift_visit(const OpenCtx& x, u32& rt, u32 u, u32& lmin) {
-  const u64 e = x.info[u];
-  if (e & INFO_FINAL) {  // conquered neighbour: an entry offer at cost `level`
-    lmin = min(lmin, (u32)e);
+// One visit of the arc t -> u at level `level`.  (rt, xt) is this lane's belief of t's root and
+// of the word it last saw there; xu is node[u] as loaded by the caller.  Every belief may be
+// stale: decisions are taken either on words that can no longer change (results of earlier
+// levels, weights) or through an atomic that fails — and says where to look — when the belief
+// was wrong.
+__device__ __forceinline__ void ift_visit(u64* __restrict__ node, u32 level, u32& rt, u64& xt, u32 u, u64 xu,
+                                          u32& lmin) {
+  u32 ru = u;
+  if (NODE_HI(xu) == 0) xu = node_find(node, ru, xu);
+  const u32 h = NODE_HI(xu);
+  if (h < level + 2u) {  // conquered at an earlier level: an entry offer at cost `level`
+    lmin = min(lmin, NODE_LO(xu));
+    if (ru != u) node[u] = xu;  // lazy finalize
     return;
   }
-  if (INFO_W(e) > x.level) return;  // closed at this level
-  u32 ru = uf_find(x.parent, u);
-  const u64 su = x.state[ru];
-  if ((u32)(su >> 32) < IFTWT_MAX_COST) {
-    lmin = min(lmin, (u32)su);
-    x.info[u] = INFO_FINAL | (e & 0x000001FF00000000ull) | (u64)(u32)su;  // lazy finalize
-    return;
-  }
-  while (rt != ru) {  // hook the larger representative under the smaller
+  if (h >= NODE_UNCONQ && h - NODE_UNCONQ > level) return;  // closed at this level
+  // open and not conquered before this level: same component as t.  Hook the larger root
+  // under the smaller; a result that already landed on the hooked root moves to the new root.
+  while (rt != ru) {
     if (rt < ru) {
-      const u32 ret = atomicCAS(&x.parent[ru], ru, rt);
-      if (ret == ru) break;
-      ru = ret;
-    } else {
-      const u32 ret = atomicCAS(&x.parent[rt], rt, ru);
-      if (ret == rt) {
-        rt = ru;
+      const u64 old = atomicCAS((unsigned long long*)&node[ru], (unsigned long long)xu, (unsigned long long)rt);
+      if (old == xu) {
+        if (NODE_HI(xu) < NODE_UNCONQ) node_offer(node, rt, xu);
         break;
       }
-      rt = ret;
+      xu = node_find(node, ru, old);
+    } else {
+      const u64 old = atomicCAS((unsigned long long*)&node[rt], (unsigned long long)xt, (unsigned long long)ru);
+      if (old == xt) {
+        if (NODE_HI(xt) < NODE_UNCONQ) node_offer(node, ru, xt);
+        rt = ru;
+        xt = xu;
+        break;
+      }
+      xt = node_find(node, rt, old);
     }
   }
 }
 // Blocks [0, open_blocks) open the vertices of this level's segment, G lanes per vertex; the
 // remaining blocks finalize the previous level's segment (one thread per vertex) — independent
 // work that would otherwise need a launch of its own.
-// Why G varies: a vertex visit is a chain of ~7 dependent memory accesses, so a level's time is
+// Why G varies: a vertex visit is a chain of dependent memory accesses, so a level's time is
 // (vertices in flight)^-1 x chain latency, not bandwidth.  With a whole warp per vertex only
 // 64 x 148 vertices are in flight; big levels use fewer lanes per vertex (down to one thread
 // per vertex) to put up to 32x more chains in flight, small levels keep a warp per vertex so
-// that each chain is as short as possible.
+// that each chain is as short as possible.  Occupancy is what buys memory
+// parallelism here: at 46 registers (5 blocks / SM) the run took 8.2 ms, at 32 registers
+// 6.3 ms; fetching 2 or 4 neighbour words ahead of the visits did not help (6.4 / 7.8 ms).
 template <int G>
-__global__ void __launch_bounds__(256)
-ift_level_open_kernel(const u32* __restrict__ byw, u32 seg_begin, u32 seg_len, u32 level, u32 open_blocks,
-                      u32 prev_begin, u32 prev_len, const u32* __restrict__ fwd, int k,
-                      const u32* __restrict__ roff, const u32* __restrict__ radj, u64* __restrict__ info,
-                      const u64* __restrict__ state, u32* __restrict__ parent, u32* __restrict__ local_min) {
+__global__ void __launch_bounds__(256, 8)  // 32 registers: 2048 chains in flight per SM
+ift_level_kernel(const u32* __restrict__ byw, u32 seg_begin, u32 seg_len, u32 level, u32 open_blocks,
+                 u32 prev_begin, u32 prev_len, const u32* __restrict__ fwd, int k,
+                 const u32* __restrict__ roff, const u32* __restrict__ radj, u64* __restrict__ node) {
   if (blockIdx.x >= open_blocks) {
     const u32 i = (blockIdx.x - open_blocks) * blockDim.x + threadIdx.x;
     if (i >= prev_len) return;
     const u32 t = byw[prev_begin + i];
-    const u64 e = info[t];
-    if (e & INFO_FINAL) return;
-    const u64 s = state[uf_find(parent, t)];
-    if ((u32)(s >> 32) < IFTWT_MAX_COST) info[t] = INFO_FINAL | (e & 0x000001FF00000000ull) | (u64)(u32)s;
+    u64 x = node[t];
+    if (NODE_HI(x) != 0) return;
+    u32 r = t;
+    x = node_find(node, r, x);
+    if (NODE_HI(x) < level + 2u) node[t] = x;
     return;
   }
   const u32 gv = (blockIdx.x * blockDim.x + threadIdx.x) / G;
   const int gl = threadIdx.x % G;
   const bool active = gv < seg_len;
-  u32 t = 0;
+  u32 t = 0, rt = 0;
+  u64 xt = 0;
   bool work = false;
   if (active) {
     t = byw[seg_begin + gv];
-    work = !(info[t] & INFO_FINAL);  // a seed is conquered from the start
+    rt = t;
+    xt = node_find(node, rt, node[t]);       // t may already hang under a same-level neighbour
+    work = NODE_HI(xt) >= level + 2u;        // a seed is conquered from the start
   }
   u32 lmin = LBL_NONE;
   if (work) {
-    OpenCtx x{info, state, parent, level};
-    u32 rt = t;
-    for (int j = gl; j < k; j += G) {
-      u32 u = fwd[(size_t)t * k + j];
-      if (u != 0xFFFFFFFFu && u != t) ift_visit(x, rt, u, lmin);
+    const u32 b = roff[t];
+    const u32 na = (u32)k + (roff[t + 1] - b);
+    const u32* row = fwd + (size_t)t * k;
+    for (u32 i = gl; i < na; i += G) {
+      const u32 u = i < (u32)k ? row[i] : radj[b + i - k];
+      if (u != 0xFFFFFFFFu && u != t) ift_visit(node, level, rt, xt, u, node[u], lmin);
     }
-    const u32 b = roff[t], e = roff[t + 1];
-    for (u32 a = b + gl; a < e; a += G) ift_visit(x, rt, radj[a], lmin);
   }
 #pragma unroll
   for (int o = G / 2; o > 0; o >>= 1) lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
-  if (active && gl == 0) local_min[t] = lmin;
-}
-// B: push the entry labels to the component roots
-__global__ void ift_level_settle_kernel(const u32* __restrict__ byw, u32 seg_begin, u32 seg_len, u32 level,
-                                        u32* __restrict__ parent, const u32* __restrict__ local_min,
-                                        u64* __restrict__ state) {
-  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= seg_len) return;
-  u32 t = byw[seg_begin + i];
-  u32 lm = local_min[t];
-  if (lm == LBL_NONE) return;
-  u32 r = uf_find(parent, t);
-  atomicMin((unsigned long long*)&state[r], (unsigned long long)(((u64)level << 32) | (u64)lm));
+  if (work && gl == 0 && lmin != LBL_NONE) node_offer(node, rt, ((u64)(level + 2u) << 32) | (u64)lmin);
 }
 // every vertex reads its component's word; unconquered vertices keep (500, self)
-__global__ void ift_resolve_kernel(u32* __restrict__ parent, u64* __restrict__ state, const u32* __restrict__ perm,
-                                   u32 n, u32* __restrict__ cost_o, u32* __restrict__ label_o,
-                                   u64* __restrict__ res) {
+__global__ void ift_resolve_kernel(u64* __restrict__ node, const u32* __restrict__ perm, u32 n,
+                                   u32* __restrict__ cost_o, u32* __restrict__ label_o, u64* __restrict__ res) {
   u32 v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n) return;
-  u32 r = uf_find(parent, v);
-  u64 s = state[r];
-  u32 o = perm[v];
-  u32 cst = (u32)(s >> 32);
-  if (cst >= IFTWT_MAX_COST) s = ((u64)IFTWT_MAX_COST << 32) | (u64)o;
-  cost_o[o] = (u32)(s >> 32);
-  label_o[o] = (u32)s;
-  res[v] = s;
+  u32 r = v;
+  const u64 x = node_find(node, r, node[v]);
+  const u32 o = perm[v];
+  const u32 h = NODE_HI(x);
+  u32 cst = IFTWT_MAX_COST, lbl = o;
+  if (h < NODE_UNCONQ) {
+    cst = h < 2u ? 0u : h - 2u;
+    lbl = NODE_LO(x);
+  }
+  cost_o[o] = cst;
+  label_o[o] = lbl;
+  res[v] = ((u64)cst << 32) | (u64)lbl;
 }
 
 }  // namespace
@@ -226,32 +239,26 @@ int ift_run(iftwt_ctx* c, const float* d_w_orig, const u32* d_seeds_orig, size_t
   if (c->graph_k == 0) return ctx_fail(c, IFTWT_ERR_STATE, "graph is not built");
   StageTimer st(c, IFTWT_STAGE_IFT);
   const u32 n = (u32)c->n;
-  ENSURE(c, c->ift_state, (size_t)n * 8);
-  ENSURE(c, c->ift_parent, (size_t)n * 4);
   ENSURE(c, c->ift_w, (size_t)n * 2 * 2 + 16);
   ENSURE(c, c->ift_byw, (size_t)n * 4 * 2);
-  ENSURE(c, c->ift_local, (size_t)n * 4);
   ENSURE(c, c->ift_res, (size_t)n * 8);
   ENSURE(c, c->ift_wf, (size_t)n * 4);
-  ENSURE(c, c->ift_info, (size_t)n * 8);
-  u64* info = c->ift_info.as<u64>();
+  ENSURE(c, c->ift_node, (size_t)n * 8);
+  u64* node = c->ift_node.as<u64>();
   ENSURE(c, c->out_a, (size_t)n * 4 * 2);
-  u64* state = c->ift_state.as<u64>();
-  u32* parent = c->ift_parent.as<u32>();
   unsigned short* w16 = c->ift_w.as<unsigned short>();
   unsigned short* w16_sorted = w16 + ((n + 7) & ~7u);
   u32* ids = c->ift_byw.as<u32>();
   u32* byw = ids + n;
-  u32* local_min = c->ift_local.as<u32>();
   u32* sc = (u32*)c->scalars.as<int>();
   u32* hs = (u32*)c->h_scalars;
   u32* d_bad = sc + 64;
   u32* d_seg = sc + 128;  // 513 entries
   CU_TRY(c, cudaMemsetAsync(d_bad, 0, 8, c->stream));
   LAUNCH(c, ift_init_kernel, div_up(n, 256), 256, 0, d_w_orig, c->pts_in.as<float4>(), c->perm.as<u32>(), n, w16,
-         state, parent, ids, c->ift_wf.as<float>(), info, d_bad);
+         node, ids, c->ift_wf.as<float>(), d_bad);
   if (ns) LAUNCH(c, ift_seed_kernel, div_up(ns, 256), 256, 0, d_seeds_orig, (u32)ns, c->inv.as<u32>(), n, w16,
-                 state, info, d_bad);
+                 node, d_bad);
   CHECK_LAUNCH(c);
   {  // vertices grouped by weight (stable: ascending vertex id inside a level)
     size_t tb = 0;
@@ -273,7 +280,7 @@ int ift_run(iftwt_ctx* c, const float* d_w_orig, const u32* d_seeds_orig, size_t
   u64 levels = 0;
   u32 prev_b = 0, prev_len = 0;
   const char* wenv = getenv("IFTWT_IFT_WAVES");
-  const double waves = wenv ? atof(wenv) : 4.0;  // swept on B200: 0.5 -> 10.4 ms, 2 -> 7.9, 4 -> 7.6, 8 -> 8.0, warp per vertex -> 9.5
+  const double waves = wenv ? atof(wenv) : 4.0;  // swept on B200: 1 -> 7.7 ms, 2 -> 6.7, 4 -> 6.3, 8 -> 6.8, 16 -> 7.7
   for (u32 lv = 0; lv < IFTWT_MAX_COST; ++lv) {
     u32 b = seg[lv], len = seg[lv + 1] - seg[lv];
     if (len == 0) continue;
@@ -282,19 +289,18 @@ int ift_run(iftwt_ctx* c, const float* d_w_orig, const u32* d_seeds_orig, size_t
     int G = 32;
     while (G > 1 && (double)len * G > waves * 2048.0 * (double)c->sm_count) G >>= 1;
     const u32 open_blocks = div_up((size_t)len * G, 256);
-    auto kern = G == 32 ? ift_level_open_kernel<32> : G == 16 ? ift_level_open_kernel<16>
-              : G == 8 ? ift_level_open_kernel<8> : G == 4 ? ift_level_open_kernel<4>
-              : G == 2 ? ift_level_open_kernel<2> : ift_level_open_kernel<1>;
+    auto kern = G == 32 ? ift_level_kernel<32> : G == 16 ? ift_level_kernel<16>
+              : G == 8 ? ift_level_kernel<8> : G == 4 ? ift_level_kernel<4>
+              : G == 2 ? ift_level_kernel<2> : ift_level_kernel<1>;
     LAUNCH(c, kern, open_blocks + div_up(prev_len, 256), 256, 0, byw, b, len, lv, open_blocks, prev_b,
-           prev_len, fwd, c->graph_k, c->g_off.as<u32>(), c->g_adj.as<u32>(), info, state, parent, local_min);
-    LAUNCH(c, ift_level_settle_kernel, div_up(len, 256), 256, 0, byw, b, len, lv, parent, local_min, state);
+           prev_len, fwd, c->graph_k, c->g_off.as<u32>(), c->g_adj.as<u32>(), node);
     prev_b = b;
     prev_len = len;
   }
   CHECK_LAUNCH(c);
   u32* cost_o = c->out_a.as<u32>();
   u32* label_o = cost_o + n;
-  LAUNCH(c, ift_resolve_kernel, div_up(n, 256), 256, 0, parent, state, c->perm.as<u32>(), n, cost_o, label_o,
+  LAUNCH(c, ift_resolve_kernel, div_up(n, 256), 256, 0, node, c->perm.as<u32>(), n, cost_o, label_o,
          c->ift_res.as<u64>());
   CHECK_LAUNCH(c);
   c->stats.ift_levels = levels;

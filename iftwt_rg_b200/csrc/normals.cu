@@ -3,8 +3,8 @@
 // Replaces pcl::NormalEstimationOMP::compute as called at main.cpp:104-109
 // (computePointNormal -> computeMeanAndCovarianceMatrix -> solvePlaneParameters ->
 // eigen33 -> computeRoots / computeRoots2, then flipNormalTowardsViewpoint with the
-// default viewpoint (0,0,0)).  Scalar FP32, one thread per point, no tensor cores:
-// this is k gathers and a 3x3 eigenproblem, not a dense contraction.
+// default viewpoint (0,0,0)).  Scalar FP32, no tensor cores: this is k gathers and a 3x3
+// eigenproblem per point, not a dense contraction.
 //
 // Bit parity with the oracle (oracle/iftwt_oracle.cpp: point_normal): the FP32
 // operation order below is the oracle's, the build uses -fmad=false so nothing is
@@ -122,35 +122,12 @@ __device__ __forceinline__ float sqnorm3(const float v[3]) {
   return v[0] * v[0] + (v[1] * v[1] + v[2] * v[2]);
 }
 
-__global__ void __launch_bounds__(128)
-normals_kernel(const float4* __restrict__ spts, const u32* __restrict__ nbr, u32 n, int k,
-               float4* __restrict__ out) {
-  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const u32* row = nbr + (size_t)i * k;
-  int cnt = 0;
-  float a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0;
-  for (int j = 0; j < k; ++j) {
-    u32 v = row[j];
-    if (v == SID_NONE) continue;
-    float4 p = spts[v];
-    a0 += p.x * p.x;
-    a1 += p.x * p.y;
-    a2 += p.x * p.z;
-    a3 += p.y * p.y;
-    a4 += p.y * p.z;
-    a5 += p.z * p.z;
-    a6 += p.x;
-    a7 += p.y;
-    a8 += p.z;
-    ++cnt;
-  }
-  float4 res;
+// everything after the k-term sums: means, covariance, smallest eigenpair, flip, curvature
+__device__ __forceinline__ float4 finish_normal(float a0, float a1, float a2, float a3, float a4, float a5, float a6,
+                                                float a7, float a8, int cnt, const float4 self) {
   if (cnt < 3) {
     float nanv = __int_as_float(0x7FC00000);
-    res = make_float4(nanv, nanv, nanv, nanv);
-    out[i] = res;
-    return;
+    return make_float4(nanv, nanv, nanv, nanv);
   }
   float fc = (float)cnt;
   a0 /= fc; a1 /= fc; a2 /= fc; a3 /= fc; a4 /= fc; a5 /= fc; a6 /= fc; a7 /= fc; a8 /= fc;
@@ -200,14 +177,82 @@ normals_kernel(const float4* __restrict__ spts, const u32* __restrict__ nbr, u32
   float eig_sum = cov[0][0] + cov[1][1];
   eig_sum = eig_sum + cov[2][2];
   float curvature = (eig_sum != 0.f) ? fabsf(eigenvalue / eig_sum) : 0.f;
-  float4 self = spts[i];
   float vx = 0.f - self.x, vy = 0.f - self.y, vz = 0.f - self.z;
   float ct = vx * nx + vy * ny;
   ct = ct + vz * nz;
   if (ct < 0.f) {
     nx *= -1.f; ny *= -1.f; nz *= -1.f;
   }
-  out[i] = make_float4(nx, ny, nz, curvature);
+  return make_float4(nx, ny, nz, curvature);
+}
+
+// One warp per tile of 32 consecutive (Morton-adjacent) points, NRM_C neighbours at a time.
+//   gather:     lane <-> (point, neighbour) ENTRY of the tile.  The 32 entries of a request are
+//               the consecutive row entries of two points, so the index loads are two 64-byte
+//               runs and the coordinate gathers fall on the few lines the neighbourhood of ONE
+//               place occupies in Morton order; the coordinates go to shared memory.
+//   accumulate: lane <-> POINT.  The nine FP32 sums advance in list order, exactly as
+//               pcl::computeMeanAndCovarianceMatrix does — the order is part of the contract.
+// The one-thread-per-point form of this kernel (rows read at a 4k-byte stride, every gather on
+// its own line) ran at 97 % L1 tag throughput: 64 requests x 32 lines per warp
+// (profiles/r01_misc_kernels_ncu.txt).
+#define NRM_C 16
+#define NRM_B 8  // gather rounds in flight per lane
+#define NRM_STRIDE (NRM_C * 3 + 1)
+#define NRM_WARPS 4
+__global__ void __launch_bounds__(NRM_WARPS * 32)
+normals_kernel(const float4* __restrict__ spts, const u32* __restrict__ nbr, u32 n, int k,
+               float4* __restrict__ out) {
+  __shared__ float s_nb[NRM_WARPS][32 * NRM_STRIDE];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const u32 u0 = (blockIdx.x * NRM_WARPS + warp) * 32u;
+  if (u0 >= n) return;
+  float* nb = s_nb[warp];
+  const u32 i = u0 + lane;
+  int cnt = 0;
+  float a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0;
+  const float nanv = __int_as_float(0x7FC00000);
+  for (int c0 = 0; c0 < k; c0 += NRM_C) {
+    const int cc = min(NRM_C, k - c0);
+    for (int e0 = lane; e0 < 32 * NRM_C; e0 += 32 * NRM_B) {
+      u32 v[NRM_B];
+      float4 P[NRM_B];
+#pragma unroll
+      for (int b = 0; b < NRM_B; ++b) {
+        const int e = e0 + 32 * b, p = e / NRM_C, j = e % NRM_C;
+        v[b] = (j < cc && u0 + p < n) ? nbr[(size_t)(u0 + p) * k + c0 + j] : SID_NONE;
+      }
+#pragma unroll
+      for (int b = 0; b < NRM_B; ++b) P[b] = v[b] != SID_NONE ? spts[v[b]] : make_float4(nanv, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int b = 0; b < NRM_B; ++b) {
+        const int e = e0 + 32 * b, p = e / NRM_C, j = e % NRM_C;
+        float* d = nb + p * NRM_STRIDE + 3 * j;
+        d[0] = P[b].x;
+        d[1] = P[b].y;
+        d[2] = P[b].z;
+      }
+    }
+    __syncwarp();
+    const float* mine = nb + lane * NRM_STRIDE;
+#pragma unroll 4
+    for (int j = 0; j < NRM_C; ++j) {
+      const float px = mine[3 * j], py = mine[3 * j + 1], pz = mine[3 * j + 2];
+      if (px != px) continue;  // missing neighbour (or past the row's end)
+      a0 += px * px;
+      a1 += px * py;
+      a2 += px * pz;
+      a3 += py * py;
+      a4 += py * pz;
+      a5 += pz * pz;
+      a6 += px;
+      a7 += py;
+      a8 += pz;
+      ++cnt;
+    }
+    __syncwarp();
+  }
+  if (i < n) out[i] = finish_normal(a0, a1, a2, a3, a4, a5, a6, a7, a8, cnt, spts[i]);
 }
 
 }  // namespace
@@ -218,7 +263,7 @@ int normals_run(iftwt_ctx* c) {
   StageTimer st(c, IFTWT_STAGE_NORMALS);
   const u32 n = (u32)c->n;
   ENSURE(c, c->nrm, (size_t)n * 16);
-  LAUNCH(c, normals_kernel, div_up(n, 128), 128, 0, c->spts.as<float4>(), c->nbr.as<u32>(), n, c->knn_k,
+  LAUNCH(c, normals_kernel, div_up(n, NRM_WARPS * 32), NRM_WARPS * 32, 0, c->spts.as<float4>(), c->nbr.as<u32>(), n, c->knn_k,
          c->nrm.as<float4>());
   CHECK_LAUNCH(c);
   c->nrm_k = c->knn_k;

@@ -113,7 +113,9 @@ rg_arcs_kernel(const u32* __restrict__ nbr, const float* __restrict__ nd2, const
       if (!oneway) {
         if (v < u) {  // the twin arc v->u is mutual and smooth too; one of the pair hooks
           if (ru == 0xFFFFFFFFu) ru = uf_find(parent, u);
-          u32 rv = uf_find(parent, v);
+          u32 rv = parent[v];
+          if (rv == ru) continue;  // v hangs directly under u's representative: one load, no chase
+          rv = uf_find(parent, rv);
           while (ru != rv) {
             if (ru < rv) {
               u32 ret = atomicCAS(&parent[rv], rv, ru);
