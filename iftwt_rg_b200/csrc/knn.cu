@@ -79,9 +79,8 @@ __device__ __forceinline__ void cell_queries(const CellWarp& w, const float* __r
 #pragma unroll
     for (int r = 0; r < RR; ++r) {
       const int slot = lane + 32 * r;
-      const float4 P = w.s_pts[slot];  // slots >= M hold stale but finite data; masked below
-      const float dd = dist2_exact(Q.x, Q.y, Q.z, P.x, P.y, P.z);
-      d[r] = slot < M ? dd : INFINITY;
+      const float4 P = w.s_pts[slot];  // slots >= M hold +inf coordinates: their distance is +inf
+      d[r] = dist2_exact(Q.x, Q.y, Q.z, P.x, P.y, P.z);
     }
     // ---- threshold search: k <= #{d < tau} <= CS (candidate count ~ linear in tau on a surface) ----
     int cnt = M;
@@ -271,11 +270,11 @@ knn_cell_kernel(GridView g, const float4* __restrict__ spts, const float* __rest
       s_id[o + t] = s + t;
     }
   }
-  // the compiled round count covers the staged rounds; unstaged slots it touches must hold
-  // finite coordinates (they are masked, not skipped)
+  // the compiled round count covers the staged rounds; the unstaged slots it touches hold +inf
+  // coordinates, so their distance is +inf and no threshold ever admits them
   const int R = (M + 31) >> 5;
   const int RRu = R <= KNN_RR_SMALL(E) ? KNN_RR_SMALL(E) : KNN_RR_MAX(E);
-  for (int t = M + lane; t < RRu * 32; t += 32) s_pts[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = M + lane; t < RRu * 32; t += 32) s_pts[t] = make_float4(INFINITY, INFINITY, INFINITY, 0.f);
   __syncwarp();
 
   CellWarp w;
