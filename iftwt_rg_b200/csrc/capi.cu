@@ -179,7 +179,7 @@ void iftwt_destroy(iftwt_ctx* c) {
                     &c->tmp, &c->scalars, &c->cell_key, &c->cell_cnt, &c->cell_start, &c->hkeys, &c->hvals,
                     &c->qb2, &c->nbr, &c->nd2, &c->kth, &c->fb_list, &c->g_off, &c->g_adj, &c->g_deg, &c->g_fwd,
                     &c->ow_mask, &c->nrm, &c->vx_keys, &c->vx_rows, &c->vx_cent, &c->vx_hk, &c->vx_hv, &c->ift_res, &c->ift_wf, &c->ift_node, &c->h_keys, &c->h_vals, &c->h_pairs, &c->h_seeds, &c->h_info,
-                    &c->rg_rank, &c->rg_parent, &c->rg_label, &c->rg_aux, &c->rg_aux2, &c->seeds, &c->ift_w,
+                    &c->rg_rank, &c->rg_parent, &c->rg_label, &c->rg_aux, &c->rg_aux2, &c->rg_masks, &c->seeds, &c->ift_w,
                     &c->ift_byw, &c->out_a, &c->out_b};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);

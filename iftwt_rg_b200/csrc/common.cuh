@@ -85,7 +85,7 @@ struct iftwt_ctx {
   int nrm_k = 0;
   DevBuf nrm;  // float4 [n] sorted space {nx,ny,nz,curv}
   // --- seeds ---
-  DevBuf rg_rank, rg_parent, rg_label, rg_aux, rg_aux2;
+  DevBuf rg_rank, rg_parent, rg_label, rg_aux, rg_aux2, rg_masks;
   DevBuf seeds;  // u32 [n_seeds] orig indices
   size_t n_seeds = 0;
   bool seeds_valid = false;

@@ -172,6 +172,9 @@ __device__ __forceinline__ void ift_visit(u64* __restrict__ node, u32 level, u32
 // that each chain is as short as possible.  Occupancy is what buys memory
 // parallelism here: at 46 registers (5 blocks / SM) the run took 8.2 ms, at 32 registers
 // 6.3 ms; fetching 2 or 4 neighbour words ahead of the visits did not help (6.4 / 7.8 ms).
+// Measured and rejected as well: streaming (evict-first) row loads (6.28 vs 6.23 ms) and a
+// persisting-L2 window over node[] — the carve-out it needs slowed every other stage (grid
+// 1.4 -> 2.5 ms) and the IFT itself (6.2 -> 7.9 ms).
 template <int G>
 __global__ void __launch_bounds__(256, 8)  // 32 registers: 2048 chains in flight per SM
 ift_level_kernel(const u32* __restrict__ byw, u32 seg_begin, u32 seg_len, u32 level, u32 open_blocks,
@@ -205,9 +208,25 @@ ift_level_kernel(const u32* __restrict__ byw, u32 seg_begin, u32 seg_len, u32 le
     const u32 b = roff[t];
     const u32 na = (u32)k + (roff[t + 1] - b);
     const u32* row = fwd + (size_t)t * k;
-    for (u32 i = gl; i < na; i += G) {
-      const u32 u = i < (u32)k ? row[i] : radj[b + i - k];
-      if (u != 0xFFFFFFFFu && u != t) ift_visit(node, level, rt, xt, u, node[u], lmin);
+    if (G == 32) {
+      // a warp per vertex runs at most a few rounds: fetch two rounds of neighbour words before
+      // working on either (the visits hold atomics the compiler cannot move loads across)
+      for (u32 i = gl; i < na; i += 2 * G) {
+        const u32 i1 = i + G;
+        u32 u0 = i < (u32)k ? row[i] : radj[b + i - k];
+        u32 u1 = i1 < na ? (i1 < (u32)k ? row[i1] : radj[b + i1 - k]) : 0xFFFFFFFFu;
+        if (u0 == t) u0 = 0xFFFFFFFFu;
+        if (u1 == t) u1 = 0xFFFFFFFFu;
+        const u64 x0 = u0 != 0xFFFFFFFFu ? node[u0] : 0ull;
+        const u64 x1 = u1 != 0xFFFFFFFFu ? node[u1] : 0ull;
+        if (u0 != 0xFFFFFFFFu) ift_visit(node, level, rt, xt, u0, x0, lmin);
+        if (u1 != 0xFFFFFFFFu) ift_visit(node, level, rt, xt, u1, x1, lmin);
+      }
+    } else {
+      for (u32 i = gl; i < na; i += G) {
+        const u32 u = i < (u32)k ? row[i] : radj[b + i - k];
+        if (u != 0xFFFFFFFFu && u != t) ift_visit(node, level, rt, xt, u, node[u], lmin);
+      }
     }
   }
 #pragma unroll

@@ -66,76 +66,168 @@ __global__ void scatter_rank_kernel(const u32* __restrict__ sorted_vals, u32 n, 
   rank[sorted_vals[r]] = r;
 }
 
-// One thread per vertex u (ECL-CC style): the smooth MUTUAL arcs to smaller ids are
-// hooked into the union-find with u's representative cached in a register (no two lanes of a
-// warp fight over the same root: a warp-per-vertex variant of this kernel spent 19 ms in CAS
-// retries); the smooth ONE-WAY arcs are remembered in a bit mask and appended to
-// (arc_u, arc_v) with one global atomic per block.
-// FUSED (iftwt_segment, one shared neighbourhood size): the same pass also decides mutuality
-// itself — one gather of the neighbour's k-th key per arc — and leaves ow_mask / rdeg / n_fwd
-// for graph_build, so the rows and the neighbours are visited once instead of twice.
+// Region-growing arcs in two kernels.
+//
+// rg_classify_kernel — one warp per tile of 32 consecutive (Morton-adjacent) vertices, one lane
+// per ENTRY (vertex, j) of the tile's 32 x k row block.  The 32 entries of a request are
+// consecutive in memory (coalesced index / distance loads) and are the neighbours of one or
+// two vertices, so the gathers of the neighbour's normal and k-th key fall on the few lines one
+// neighbourhood occupies in Morton order.  RGA_B rounds of loads are in flight per lane.  Per
+// entry: valid, one-way (u is not among the k nearest of v), smooth; per vertex three bit masks
+// leave the kernel: one-way arcs (graph.cu's ow_mask), smooth MUTUAL arcs to smaller ids (to be
+// hooked), smooth ONE-WAY arcs (to be listed).
+// FUSED (iftwt_segment, one shared neighbourhood size): the pass also decides mutuality itself
+// — one gather of the neighbour's k-th key per arc — and leaves ow_mask / rdeg / n_fwd for
+// graph_build, so the rows and the neighbours are visited once instead of twice.
+//
+// rg_hook_kernel — one thread per vertex u (ECL-CC style): the arcs of the hook mask go into the
+// union-find with u's representative cached in a register (no two lanes of a warp fight over
+// the same root: a warp-per-vertex variant spent 19 ms in CAS retries); the arcs of the list
+// mask are appended to (arc_u, arc_v) with one global atomic per block.
+//
+// One thread per vertex doing both (rows and distances read at a 4k-byte stride, two gathers
+// per arc each on its own line, finds and CAS in between) ran at 88 % L1 throughput with 45
+// long-scoreboard stall cycles per issue: 3.9 ms at 10 M points, k = 32
+// (profiles/r01_top_kernels_ncu_full.txt).
+#define RGA_WARPS 8
+#define RGA_B 4
+__host__ __device__ inline int rga_flag_stride(int k) {  // bytes per vertex, (bytes / 4) odd
+  int w = (k + 3) / 4;
+  return 4 * (w | 1);
+}
+static size_t rga_smem_bytes(int k) { return (size_t)RGA_WARPS * (32 * 16 + 32 * 8 + 32 * rga_flag_stride(k)); }
 template <bool FUSED>
+__global__ void __launch_bounds__(RGA_WARPS * 32, 4)
+rg_classify_kernel(const u32* __restrict__ nbr, const float* __restrict__ nd2, const u64* __restrict__ kth,
+                   const float4* __restrict__ spts, u64* __restrict__ ow_mask, const float4* __restrict__ nrm, u32 n,
+                   int k, float cos_thr, u64* __restrict__ hook_mask, u64* __restrict__ list_mask,
+                   u32* __restrict__ rdeg, unsigned long long* __restrict__ n_fwd) {
+  extern __shared__ __align__(16) unsigned char rga_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fs = rga_flag_stride(k);
+  unsigned char* base = rga_smem + (size_t)warp * (32 * 16 + 32 * 8 + 32 * fs);
+  float4* s_nu = (float4*)base;                            // normal of each tile vertex
+  u64* s_aux = (u64*)(base + 32 * 16);                     // FUSED: original index; else: the one-way mask
+  unsigned char* s_flags = base + 32 * 16 + 32 * 8;        // [32][fs] 1 valid | 2 one-way | 4 smooth | 8 v < u
+  const u32 u0 = (blockIdx.x * RGA_WARPS + warp) * 32u;
+  if (u0 >= n) return;  // warps are independent: no block-level barrier below
+  const u32 u = u0 + lane;
+  if (u < n) {
+    s_nu[lane] = nrm[u];
+    s_aux[lane] = FUSED ? (u64)__float_as_uint(spts[u].w) : ow_mask[u];
+  }
+  __syncwarp();
+  {
+    int p = lane / k, j = lane % k;
+    const size_t row0 = (size_t)u0 * k;
+    for (int r0 = 0; r0 < k; r0 += RGA_B) {  // 32 k entries, 32 per round
+      int pp[RGA_B], jj[RGA_B];
+      u32 v[RGA_B];
+      float d2[RGA_B];
+      u64 kk[RGA_B];
+      float4 nv[RGA_B];
+      bool ok[RGA_B];
+#pragma unroll
+      for (int b = 0; b < RGA_B; ++b) {
+        pp[b] = p;
+        jj[b] = j;
+        const u32 e = (u32)lane + 32u * (u32)(r0 + b);
+        ok[b] = r0 + b < k && u0 + (u32)p < n;
+        v[b] = ok[b] ? nbr[row0 + e] : SID_NONE;
+        d2[b] = (FUSED && ok[b]) ? nd2[row0 + e] : 0.f;
+        j += 32;
+        while (j >= k) {
+          j -= k;
+          ++p;
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < RGA_B; ++b) {
+        const bool live = v[b] != SID_NONE && v[b] != u0 + (u32)pp[b];
+        kk[b] = (FUSED && live) ? kth[v[b]] : 0ull;
+        nv[b] = live ? nrm[v[b]] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int b = 0; b < RGA_B; ++b) {
+        if (!ok[b]) continue;
+        const u32 up = u0 + (u32)pp[b];
+        unsigned flag = 0;
+        if (v[b] != SID_NONE && v[b] != up) {
+          flag = 1;
+          bool oneway;
+          if (FUSED) {
+            const u64 key = ((u64)__float_as_uint(d2[b]) << 32) | s_aux[pp[b]];
+            oneway = key > kk[b];
+            if (oneway) atomicAdd(&rdeg[v[b]], 1u);
+          } else {
+            oneway = (s_aux[pp[b]] >> jj[b]) & 1ull;  // bit j: up is NOT among the k nearest of v (graph.cu)
+          }
+          if (oneway) flag |= 2;
+          if (smooth_pass(s_nu[pp[b]], nv[b], cos_thr)) flag |= 4;
+          if (v[b] < up) flag |= 8;
+        }
+        s_flags[pp[b] * fs + jj[b]] = (unsigned char)flag;
+      }
+    }
+  }
+  __syncwarp();
+  u32 valid_cnt = 0;
+  if (u < n) {
+    const unsigned char* fl = s_flags + lane * fs;
+    u64 ow = 0, hk = 0, ls = 0;
+    for (int j = 0; j < k; ++j) {
+      const unsigned f = fl[j];
+      valid_cnt += f & 1u;
+      if (f & 2u) ow |= 1ull << j;
+      if ((f & 6u) == 6u) ls |= 1ull << j;   // smooth one-way
+      if ((f & 14u) == 12u) hk |= 1ull << j;  // smooth mutual, v < u: the twin arc is mutual and smooth
+    }                                         // too; one of the pair hooks
+    if (FUSED) ow_mask[u] = ow;
+    hook_mask[u] = hk;
+    list_mask[u] = ls;
+  }
+  if (FUSED) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) valid_cnt += __shfl_xor_sync(0xffffffffu, valid_cnt, o);
+    if (lane == 0 && valid_cnt) atomicAdd(n_fwd, (unsigned long long)valid_cnt);
+  }
+}
+
 __global__ void __launch_bounds__(256)
-rg_arcs_kernel(const u32* __restrict__ nbr, const float* __restrict__ nd2, const u64* __restrict__ kth,
-               const float4* __restrict__ spts, u64* __restrict__ ow_mask, const float4* __restrict__ nrm, u32 n,
-               int k, float cos_thr, u32* __restrict__ parent, u32* __restrict__ counter, u32* __restrict__ arc_u,
-               u32* __restrict__ arc_v, u32* __restrict__ rdeg, unsigned long long* __restrict__ n_fwd) {
-  __shared__ u32 s_warp[8], s_fwd[8];
+rg_hook_kernel(const u32* __restrict__ nbr, const u64* __restrict__ hook_mask, const u64* __restrict__ list_mask,
+               u32 n, int k, u32* __restrict__ parent, u32* __restrict__ counter, u32* __restrict__ arc_u,
+               u32* __restrict__ arc_v) {
+  __shared__ u32 s_warp[8];
   __shared__ u32 s_base;
   const u32 u = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   u64 mask = 0;
-  u32 valid_cnt = 0;
   if (u < n) {
-    const float4 nu = nrm[u];
     const u32* row = nbr + (size_t)u * k;
-    u64 ow = 0;
-    u32 ou = 0;
-    if (FUSED) ou = __float_as_uint(spts[u].w);
-    else ow = ow_mask[u];  // bit j: u is NOT among the k nearest of row[j] (graph.cu)
+    u64 hk = hook_mask[u];
+    mask = list_mask[u];
     u32 ru = 0xFFFFFFFFu;
-    for (int j = 0; j < k; ++j) {
+    while (hk) {
+      const int j = __ffsll((long long)hk) - 1;
+      hk &= hk - 1;
       const u32 v = row[j];
-      if (v == SID_NONE || v == u) continue;
-      bool oneway;
-      if (FUSED) {
-        ++valid_cnt;
-        const u64 key = ((u64)__float_as_uint(nd2[(size_t)u * k + j]) << 32) | (u64)ou;
-        oneway = key > kth[v];
-        if (oneway) {
-          ow |= 1ull << j;
-          atomicAdd(&rdeg[v], 1u);
-        }
-      } else {
-        oneway = (ow >> j) & 1ull;
-      }
-      if (!smooth_pass(nu, nrm[v], cos_thr)) continue;
-      if (!oneway) {
-        if (v < u) {  // the twin arc v->u is mutual and smooth too; one of the pair hooks
-          if (ru == 0xFFFFFFFFu) ru = uf_find(parent, u);
-          u32 rv = parent[v];
-          if (rv == ru) continue;  // v hangs directly under u's representative: one load, no chase
-          rv = uf_find(parent, rv);
-          while (ru != rv) {
-            if (ru < rv) {
-              u32 ret = atomicCAS(&parent[rv], rv, ru);
-              if (ret == rv) break;
-              rv = ret;
-            } else {
-              u32 ret = atomicCAS(&parent[ru], ru, rv);
-              if (ret == ru) {
-                ru = rv;
-                break;
-              }
-              ru = ret;
-            }
+      if (ru == 0xFFFFFFFFu) ru = uf_find(parent, u);
+      u32 rv = uf_find(parent, v);
+      while (ru != rv) {
+        if (ru < rv) {
+          u32 ret = atomicCAS(&parent[rv], rv, ru);
+          if (ret == rv) break;
+          rv = ret;
+        } else {
+          u32 ret = atomicCAS(&parent[ru], ru, rv);
+          if (ret == ru) {
+            ru = rv;
+            break;
           }
+          ru = ret;
         }
-      } else {
-        mask |= 1ull << j;
       }
     }
-    if (FUSED) ow_mask[u] = ow;
   }
   // ---- block-aggregated append of the one-way arcs ----
   u32 cnt = (u32)__popcll(mask);
@@ -145,24 +237,17 @@ rg_arcs_kernel(const u32* __restrict__ nbr, const float* __restrict__ nd2, const
     u32 t = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += t;
   }
-  if (FUSED) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) valid_cnt += __shfl_xor_sync(0xffffffffu, valid_cnt, o);
-  }
   if (lane == 31) s_warp[warp] = incl;
-  if (FUSED && lane == 0) s_fwd[warp] = valid_cnt;
   __syncthreads();
   if (threadIdx.x == 0) {
-    u32 tot = 0, fw = 0;
+    u32 tot = 0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
       u32 c = s_warp[w];
       s_warp[w] = tot;
       tot += c;
-      if (FUSED) fw += s_fwd[w];
     }
     s_base = tot ? atomicAdd(counter, tot) : 0u;
-    if (FUSED && fw) atomicAdd(n_fwd, (unsigned long long)fw);
   }
   __syncthreads();
   if (mask) {
@@ -326,10 +411,17 @@ int fused_graph_rg_run(iftwt_ctx* c, const iftwt_rg_params* p) {
   CU_TRY(c, cudaMemsetAsync(d_nfwd, 0, 8, c->stream));
   CU_TRY(c, cudaMemsetAsync(c->g_deg.p, 0, ((size_t)n + 1) * 4, c->stream));
   u32* arc_u = c->rg_aux2.as<u32>();
+  ENSURE(c, c->rg_masks, (size_t)n * 16);
+  u64* hook_mask = c->rg_masks.as<u64>();
+  u64* list_mask = hook_mask + n;
   LAUNCH(c, iota_kernel, div_up(n, 256), 256, 0, c->rg_parent.as<u32>(), n);
-  LAUNCH(c, rg_arcs_kernel<true>, div_up(n, 256), 256, 0, c->nbr.as<u32>(), c->nd2.as<float>(), c->kth.as<u64>(),
-         c->spts.as<float4>(), c->ow_mask.as<u64>(), c->nrm.as<float4>(), n, k, cos_thr, c->rg_parent.as<u32>(), d_cnt,
-         arc_u, arc_u + (ne + 1), c->g_deg.as<u32>(), d_nfwd);
+  CU_TRY(c, cudaFuncSetAttribute(rg_classify_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)rga_smem_bytes(k)));
+  LAUNCH(c, rg_classify_kernel<true>, div_up(n, RGA_WARPS * 32), RGA_WARPS * 32, rga_smem_bytes(k), c->nbr.as<u32>(),
+         c->nd2.as<float>(), c->kth.as<u64>(), c->spts.as<float4>(), c->ow_mask.as<u64>(), c->nrm.as<float4>(), n, k,
+         cos_thr, hook_mask, list_mask, c->g_deg.as<u32>(), d_nfwd);
+  LAUNCH(c, rg_hook_kernel, div_up(n, 256), 256, 0, c->nbr.as<u32>(), hook_mask, list_mask, n, k,
+         c->rg_parent.as<u32>(), d_cnt, arc_u, arc_u + (ne + 1));
   CHECK_LAUNCH(c);
   c->mask_k = k;
   c->rdeg_k = k;
@@ -406,9 +498,16 @@ int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p) {
     arc_v = arc_u + (ne + 1);
     LAUNCH(c, iota_kernel, div_up(n, 256), 256, 0, parent, n);
     if (c->mask_k != c->knn_k) TRY(knn_mutual_run(c, false));
-    LAUNCH(c, rg_arcs_kernel<false>, div_up(n, 256), 256, 0, c->nbr.as<u32>(), (const float*)nullptr,
-           (const u64*)nullptr, (const float4*)nullptr, c->ow_mask.as<u64>(), nrm, n, k, cos_thr, parent, d_cnt, arc_u,
-           arc_v, (u32*)nullptr, (unsigned long long*)nullptr);
+    ENSURE(c, c->rg_masks, (size_t)n * 16);
+    u64* hook_mask = c->rg_masks.as<u64>();
+    u64* list_mask = hook_mask + n;
+    CU_TRY(c, cudaFuncSetAttribute(rg_classify_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)rga_smem_bytes(k)));
+    LAUNCH(c, rg_classify_kernel<false>, div_up(n, RGA_WARPS * 32), RGA_WARPS * 32, rga_smem_bytes(k),
+           c->nbr.as<u32>(), (const float*)nullptr, (const u64*)nullptr, (const float4*)nullptr, c->ow_mask.as<u64>(),
+           nrm, n, k, cos_thr, hook_mask, list_mask, (u32*)nullptr, (unsigned long long*)nullptr);
+    LAUNCH(c, rg_hook_kernel, div_up(n, 256), 256, 0, c->nbr.as<u32>(), hook_mask, list_mask, n, k, parent, d_cnt,
+           arc_u, arc_v);
     CHECK_LAUNCH(c);
   }
   c->rg_pre_valid = false;  // the union-find is consumed (flattened) below
