@@ -367,6 +367,7 @@ knn_general_kernel(GridView g, const float4* __restrict__ spts, const float4* __
   for (u32 it = gw; it < total; it += nw) {
     u32 row;
     int j0 = 0;
+    u64 cap = KEY_MAX;
     float4 Q;
     if (EXTERNAL) {
       row = it;
@@ -376,6 +377,10 @@ knn_general_kernel(GridView g, const float4* __restrict__ spts, const float4* __
       j0 = (int)(row >> 31);
       row &= 0x7FFFFFFFu;
       Q = spts[row];
+      // the fast path found k candidates inside the one-ring block (it only could not prove them
+      // complete): the key of its k-th bounds the true k-th from above, so nothing beyond it
+      // needs to enter the list
+      if (j0) cap = kth[row];
     }
     const double vx = ((double)Q.x - g.ox) * g.inv_cell, vy = ((double)Q.y - g.oy) * g.inv_cell,
                  vz = ((double)Q.z - g.oz) * g.inv_cell;
@@ -409,7 +414,7 @@ knn_general_kernel(GridView g, const float4* __restrict__ spts, const float4* __
             ck = make_key(dist2_exact(Q.x, Q.y, Q.z, P.x, P.y, P.z), __float_as_uint(P.w));
           }
           u64 thr = top.at_key(k - 1);
-          unsigned mask = __ballot_sync(FULL, ck < thr);
+          unsigned mask = __ballot_sync(FULL, ck < thr && ck <= cap);
           while (mask) {
             int src = __ffs(mask) - 1;
             mask &= mask - 1;
