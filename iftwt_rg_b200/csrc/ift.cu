@@ -174,7 +174,10 @@ __device__ __forceinline__ void ift_visit(u64* __restrict__ node, u32 level, u32
 // 6.3 ms; fetching 2 or 4 neighbour words ahead of the visits did not help (6.4 / 7.8 ms).
 // Measured and rejected as well: streaming (evict-first) row loads (6.28 vs 6.23 ms) and a
 // persisting-L2 window over node[] — the carve-out it needs slowed every other stage (grid
-// 1.4 -> 2.5 ms) and the IFT itself (6.2 -> 7.9 ms).
+// 1.4 -> 2.5 ms) and the IFT itself (6.2 -> 7.9 ms); a w16 pre-gather that skips the node word of
+// closed neighbours (one more link in the chain: 6.2 -> 6.5 ms); runs of consecutive small levels
+// in one cooperative launch with a grid barrier between levels and ld.cg node reads (6.34 vs
+// 6.23 ms: a barrier over 1184 resident blocks is no cheaper than a launch boundary).
 template <int G>
 __global__ void __launch_bounds__(256, 8)  // 32 registers: 2048 chains in flight per SM
 ift_level_kernel(const u32* __restrict__ byw, u32 seg_begin, u32 seg_len, u32 level, u32 open_blocks,

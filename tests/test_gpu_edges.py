@@ -109,3 +109,30 @@ def test_baseline_full_size_10m_properties(ctx):
     assert ns2 == ns and np.array_equal(cost, cost2) and np.array_equal(label, label2)
     st = ctx.stats()
     assert st["knn_fallback"] < 0.05 * n
+
+
+def test_ift_lakes_and_plateaus_are_schedule_independent(ctx):
+    """The IFT's lock-free level step (offers and hooks interleaving on one word per vertex) on
+    the inputs that stress it: a few weight levels, so every level is made of huge plateaus;
+    smooth basins that stay unconquered lakes for several levels and are then reached from many
+    sides at once; thousands of seeds.  Repeated runs must give the same words, and those must be
+    the oracle's (policy C)."""
+    pts = synth.scene_facade(1_000_000, seed=0x1F77)
+    n = len(pts)
+    rng = np.random.default_rng(5)
+    x, y = pts[:, 0], pts[:, 1]
+    basins = np.floor(3.99 * (0.5 + 0.5 * np.sin(1.7 * x) * np.cos(2.3 * y)))           # 0..3, metre-scale lakes
+    salt = (rng.random(n) < 0.15) * rng.integers(0, 3, n)
+    w = (basins + salt).astype(np.float32)
+    seeds = rng.integers(0, n, 3000).astype(np.int32)
+    seeds = seeds[basins[seeds] >= 2]                                                    # keep the basins seedless: lakes
+    ctx.set_cloud(pts)
+    off, adj = ctx.knn_graph(16)
+    runs = [ctx.ift(w, seeds) for _ in range(3)]
+    for cost, label in runs[1:]:
+        assert np.array_equal(cost, runs[0][0]) and np.array_equal(label, runs[0][1])
+    rcost, rlabel = orc.ift(off, adj, w, seeds, orc.POLICY_C)
+    assert np.array_equal(runs[0][0], rcost)
+    assert np.array_equal(runs[0][1], rlabel)
+    assert orc.ift_audit(off, adj, w, seeds, runs[0][0], runs[0][1]) == 0
+    assert (rcost < 500).mean() > 0.99
