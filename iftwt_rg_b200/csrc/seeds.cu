@@ -10,13 +10,13 @@
 //     segment(v) = min rank over all u that reach v along arcs u -> w,
 //                  w in kNN(u), |n_u . n_w| >= cos(theta),
 // rank = position in the (curvature, index) order.  It is computed here as
-//   1. ranks by one radix sort of (curvature bits, original index);
+//   1. the order as a 64-bit key per vertex (curvature bits << 32 | index), never as ranks;
 //   2. union-find over the MUTUAL smooth arcs (both u in kNN(w) and w in kNN(u);
-//      the test itself is symmetric), hooking + pointer jumping, O(log) depth;
-//   3. component min-rank, then label-min sweeps over the remaining ONE-WAY smooth
+//      the test itself is symmetric), hooking + path halving;
+//   3. component min-key, then label-min sweeps over the remaining ONE-WAY smooth
 //      arcs between components until nothing changes;
 //   4. segment sizes, the [min, max] filter, PCL's emission order (ascending seed
-//      rank), and the literal FP32 centroid: pcl::compute3DCentroid sums a
+//      key: a sort of the kept clusters only), and the literal FP32 centroid: pcl::compute3DCentroid sums a
 //      cluster's points in ascending point index (assembleRegions order), so the
 //      members are sorted by (cluster, index) and one thread per cluster adds them
 //      sequentially;
@@ -46,26 +46,17 @@ __device__ __forceinline__ bool smooth_pass(const float4 nu, const float4 nv, fl
   return !(dp < cos_thr);  // NaN passes, as in PCL
 }
 
-// keys in ORIGINAL order so that a stable 32-bit sort on the curvature bits breaks
-// ties by ascending original index: the canonical (curvature, index) order
-__global__ void rank_keys_kernel(const float4* __restrict__ nrm, const u32* __restrict__ inv, u32 n,
-                                 u32* __restrict__ keys, u32* __restrict__ vals) {
-  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  u32 j = inv[i];
-  keys[i] = __float_as_uint(nrm[j].w);
-  vals[i] = j;
+// The (curvature, original index) order PCL's region growing seeds by is carried as a 64-bit key
+// per vertex — curvature bits (non-negative floats order as unsigned ints) << 32 | index — and
+// never materialised as ranks: only comparisons are needed, so the 10 M-pair radix sort the
+// ranks used to cost (0.55 ms) is replaced by a sort of the KEPT clusters' keys alone.
+__device__ __forceinline__ u64 rg_key(const float4* __restrict__ nrm, const float4* __restrict__ spts, u32 v) {
+  return ((u64)__float_as_uint(nrm[v].w) << 32) | (u64)__float_as_uint(spts[v].w);
 }
 __global__ void iota_kernel(u32* __restrict__ a, u32 n) {
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) a[i] = i;
 }
-__global__ void scatter_rank_kernel(const u32* __restrict__ sorted_vals, u32 n, u32* __restrict__ rank) {
-  u32 r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n) return;
-  rank[sorted_vals[r]] = r;
-}
-
 // Region-growing arcs in two kernels.
 //
 // rg_classify_kernel — one warp per tile of 32 consecutive (Morton-adjacent) vertices, one lane
@@ -266,8 +257,9 @@ rg_hook_kernel(const u32* __restrict__ nbr, const u64* __restrict__ hook_mask, c
 // root[] is a separate array: writing the root back into parent[] would race with
 // the path halving of concurrent finds, which may overwrite it with a non-root ancestor.
 // Lanes that share a root (spatial neighbours mostly do) combine before the atomic.
-__global__ void rg_flatten_kernel(u32* __restrict__ parent, const u32* __restrict__ rank, u32 n,
-                                  u32* __restrict__ root, u32* __restrict__ L) {
+__global__ void rg_flatten_kernel(u32* __restrict__ parent, const float4* __restrict__ nrm,
+                                  const float4* __restrict__ spts, u32 n, u32* __restrict__ root,
+                                  u64* __restrict__ L) {
   u32 v = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = v < n;
   const unsigned act = __ballot_sync(0xffffffffu, valid);
@@ -275,8 +267,12 @@ __global__ void rg_flatten_kernel(u32* __restrict__ parent, const u32* __restric
   u32 r = uf_find(parent, v);
   root[v] = r;
   const unsigned grp = __match_any_sync(act, r);
-  const u32 mn = __reduce_min_sync(grp, rank[v]);
-  if ((int)(threadIdx.x & 31) == __ffs(grp) - 1 && mn < *(volatile u32*)&L[r]) atomicMin(&L[r], mn);
+  const u64 key = rg_key(nrm, spts, v);
+  const u32 hi = __reduce_min_sync(grp, (u32)(key >> 32));
+  const u32 lo = __reduce_min_sync(grp, (u32)(key >> 32) == hi ? (u32)key : 0xFFFFFFFFu);
+  const u64 mn = ((u64)hi << 32) | (u64)lo;
+  if ((int)(threadIdx.x & 31) == __ffs(grp) - 1 && mn < *(volatile u64*)&L[r])
+    atomicMin((unsigned long long*)&L[r], (unsigned long long)mn);
 }
 // arcs to root space
 __global__ void rg_arcs_to_roots_kernel(const u32* __restrict__ root, u32 m, u32* __restrict__ arc_u,
@@ -287,44 +283,65 @@ __global__ void rg_arcs_to_roots_kernel(const u32* __restrict__ root, u32 m, u32
   arc_v[i] = root[arc_v[i]];
 }
 __global__ void rg_sweep_kernel(const u32* __restrict__ arc_u, const u32* __restrict__ arc_v, u32 m,
-                                u32* __restrict__ L, u32* __restrict__ changed) {
+                                u64* __restrict__ L, u32* __restrict__ changed) {
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   u32 ru = arc_u[i], rv = arc_v[i];
   if (ru == rv) return;
-  u32 a = L[ru];
+  u64 a = L[ru];
   if (a < L[rv]) {
-    atomicMin(&L[rv], a);
+    atomicMin((unsigned long long*)&L[rv], (unsigned long long)a);
     *changed = 1u;
   }
 }
-// per point: segment = L[root]; count sizes by seed rank (warp-aggregated)
-__global__ void rg_sizes_kernel(const u32* __restrict__ root, const u32* __restrict__ L, u32 n,
-                                u32* __restrict__ seg_of, u32* __restrict__ size_by_rank) {
+// per point: segment = the vertex whose key is L[root] (the segment's seed point); sizes are
+// counted at the seed vertex (warp-aggregated)
+__global__ void rg_sizes_kernel(const u32* __restrict__ root, const u64* __restrict__ L,
+                                const u32* __restrict__ inv, u32 n, u32* __restrict__ seg_of,
+                                u32* __restrict__ size_at_seed) {
   u32 v = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = v < n;
   const unsigned act = __ballot_sync(0xffffffffu, valid);
   if (!valid) return;
-  u32 s = L[root[v]];
+  const u32 s = inv[(u32)L[root[v]]];  // low half of the key = original index of the seed point
   seg_of[v] = s;
   const unsigned grp = __match_any_sync(act, s);
-  if ((int)(threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(&size_by_rank[s], (u32)__popc(grp));
+  if ((int)(threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(&size_at_seed[s], (u32)__popc(grp));
 }
-__global__ void rg_keep_flags_kernel(const u32* __restrict__ size_by_rank, u32 n, u32 min_sz, u32 max_sz,
-                                     u32* __restrict__ keep, u32* __restrict__ nseg) {
-  u32 r = blockIdx.x * blockDim.x + threadIdx.x;
-  u32 s = r < n ? size_by_rank[r] : 0u;
-  bool any = s > 0;
-  if (r < n) keep[r] = (s >= min_sz && s <= max_sz) ? 1u : 0u;
-  unsigned m = __ballot_sync(0xffffffffu, any);
-  if ((threadIdx.x & 31) == 0 && m) atomicAdd(nseg, (u32)__popc(m));
+// keep[s] for every seed vertex s; the kept seeds' (key, vertex) pairs are appended in any
+// order — the sort that follows puts them in PCL's emission order (ascending key)
+__global__ void rg_keep_flags_kernel(const u32* __restrict__ size_at_seed, const float4* __restrict__ nrm,
+                                     const float4* __restrict__ spts, u32 n, u32 min_sz, u32 max_sz,
+                                     u32* __restrict__ keep, u32* __restrict__ nseg, u32* __restrict__ n_kept,
+                                     u64* __restrict__ kept_key, u32* __restrict__ kept_vertex) {
+  u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+  u32 s = v < n ? size_at_seed[v] : 0u;
+  const bool any = s > 0;
+  const bool kp = s >= min_sz && s <= max_sz && any;
+  if (v < n) keep[v] = kp ? 1u : 0u;
+  const unsigned m = __ballot_sync(0xffffffffu, any);
+  const unsigned mk = __ballot_sync(0xffffffffu, kp);
+  const int lane = threadIdx.x & 31;
+  if (lane == 0 && m) atomicAdd(nseg, (u32)__popc(m));
+  if (mk) {
+    u32 base = 0;
+    if (lane == __ffs(mk) - 1) base = atomicAdd(n_kept, (u32)__popc(mk));
+    base = __shfl_sync(0xffffffffu, base, __ffs(mk) - 1);
+    if (kp) {
+      const u32 pos = base + (u32)__popc(mk & ((1u << lane) - 1u));
+      kept_key[pos] = rg_key(nrm, spts, v);
+      kept_vertex[pos] = v;
+    }
+  }
 }
-// kept cluster table: size of kept cluster c (c = kept_id[rank])
-__global__ void rg_kept_sizes_kernel(const u32* __restrict__ size_by_rank, const u32* __restrict__ keep,
-                                     const u32* __restrict__ kept_id, u32 n, u32* __restrict__ ksize) {
-  u32 r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n || !keep[r]) return;
-  ksize[kept_id[r]] = size_by_rank[r];
+// kept cluster c = position of its seed in ascending key order
+__global__ void rg_kept_ids_kernel(const u32* __restrict__ kept_vertex_sorted, const u32* __restrict__ size_at_seed,
+                                   u32 n_kept, u32* __restrict__ kept_id, u32* __restrict__ ksize) {
+  u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_kept) return;
+  const u32 v = kept_vertex_sorted[c];
+  kept_id[v] = c;
+  ksize[c] = size_at_seed[v];
 }
 // members in ORIGINAL order: key = kept cluster (n_kept for dropped points), value =
 // original index; a stable sort on the key groups clusters with ascending indices
@@ -454,35 +471,20 @@ int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p) {
                     "when it cannot (threshold >= 0.34, reference uses 1.0)", p->curvature_threshold);
   const float cos_thr = cosf(p->smoothness_threshold);
 
-  // 1. ranks
+  // 1. the (curvature, index) order lives in 64-bit keys computed on the fly (rg_key)
   ENSURE(c, c->keys, (size_t)n * 8);
   ENSURE(c, c->keys_alt, (size_t)n * 8);
   ENSURE(c, c->vals_alt, (size_t)n * 4);
   ENSURE(c, c->rg_rank, (size_t)n * 4);
   ENSURE(c, c->rg_parent, (size_t)n * 4);
-  ENSURE(c, c->rg_label, (size_t)n * 4);
+  ENSURE(c, c->rg_label, (size_t)n * 8);
   ENSURE(c, c->rg_aux, (size_t)n * 4 * 4);
-  u32* rank = c->rg_rank.as<u32>();
   u32* parent = c->rg_parent.as<u32>();
-  u32* L = c->rg_label.as<u32>();
+  u64* L = c->rg_label.as<u64>();
   u32* seg_of = c->rg_aux.as<u32>();
-  u32* size_by_rank = seg_of + n;
-  u32* keep = size_by_rank + n;
+  u32* size_at_seed = seg_of + n;
+  u32* keep = size_at_seed + n;
   u32* kept_id = keep + n;
-  {
-    u32* k0 = c->keys.as<u32>();
-    u32* k1 = c->keys_alt.as<u32>();
-    u32* v0 = c->vals_alt.as<u32>();
-    u32* v1 = seg_of;  // scratch
-    LAUNCH(c, rank_keys_kernel, div_up(n, 256), 256, 0, nrm, c->inv.as<u32>(), n, k0, v0);
-    size_t tb = 0;
-    CU_TRY(c, cub::DeviceRadixSort::SortPairs(nullptr, tb, k0, k1, v0, v1, (int)n, 0, 32, c->stream));
-    ENSURE(c, c->tmp, tb);
-    CU_TRY(c, cub::DeviceRadixSort::SortPairs(c->tmp.p, tb, k0, k1, v0, v1, (int)n, 0, 32, c->stream));
-    c->stats.kernel_launches += 5;
-    LAUNCH(c, scatter_rank_kernel, div_up(n, 256), 256, 0, v1, n, rank);
-    CHECK_LAUNCH(c);
-  }
   // 2. mutual smooth arcs -> union-find; one-way smooth arcs -> list (worst-case capacity).
   //    Already done when iftwt_segment ran the fused graph + region-growing pass.
   u32* d_cnt = sc + 56;
@@ -513,9 +515,9 @@ int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p) {
   c->rg_pre_valid = false;  // the union-find is consumed (flattened) below
   CU_TRY(c, cudaMemcpyAsync(hs + 56, d_cnt, 4, cudaMemcpyDeviceToHost, c->stream));
   // 3. component min rank, then label-min over one-way arcs
-  CU_TRY(c, cudaMemsetAsync(L, 0xFF, (size_t)n * 4, c->stream));
+  CU_TRY(c, cudaMemsetAsync(L, 0xFF, (size_t)n * 8, c->stream));
   u32* root = c->vals_alt.as<u32>();  // free again once the ranks are scattered
-  LAUNCH(c, rg_flatten_kernel, div_up(n, 256), 256, 0, parent, rank, n, root, L);
+  LAUNCH(c, rg_flatten_kernel, div_up(n, 256), 256, 0, parent, nrm, spts, n, root, L);
   CHECK_LAUNCH(c);
   CU_TRY(c, cudaStreamSynchronize(c->stream));
   const u32 n_oneway = hs[56];
@@ -537,27 +539,39 @@ int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p) {
     }
   }
   c->stats.rg_sweeps = sweeps;
-  // 4. sizes, filter, emission order
-  CU_TRY(c, cudaMemsetAsync(size_by_rank, 0, (size_t)n * 4, c->stream));
-  CU_TRY(c, cudaMemsetAsync(sc + 61, 0, 4, c->stream));
-  LAUNCH(c, rg_sizes_kernel, div_up(n, 256), 256, 0, root, L, n, seg_of, size_by_rank);
-  LAUNCH(c, rg_keep_flags_kernel, div_up(n, 256), 256, 0, size_by_rank, n, (u32)max(p->min_cluster_size, 0),
-         (u32)max(p->max_cluster_size, 0), keep, sc + 61);
+  // 4. sizes, filter, emission order (ascending key of the seed point = PCL's)
+  CU_TRY(c, cudaMemsetAsync(size_at_seed, 0, (size_t)n * 4, c->stream));
+  CU_TRY(c, cudaMemsetAsync(sc + 61, 0, 8, c->stream));  // [61] segments, [62] kept
+  LAUNCH(c, rg_sizes_kernel, div_up(n, 256), 256, 0, root, L, c->inv.as<u32>(), n, seg_of, size_at_seed);
+  u64* kept_key = c->keys.as<u64>();
+  u64* kept_key_sorted = c->keys_alt.as<u64>();
+  u32* kept_vertex = c->rg_rank.as<u32>();
+  LAUNCH(c, rg_keep_flags_kernel, div_up(n, 256), 256, 0, size_at_seed, nrm, spts, n,
+         (u32)max(p->min_cluster_size, 0), (u32)max(p->max_cluster_size, 0), keep, sc + 61, sc + 62, kept_key,
+         kept_vertex);
   CHECK_LAUNCH(c);
-  {
-    size_t tb = 0;
-    CU_TRY(c, cub::DeviceScan::ExclusiveSum(nullptr, tb, keep, kept_id, (int)n, c->stream));
-    ENSURE(c, c->tmp, tb);
-    CU_TRY(c, cub::DeviceScan::ExclusiveSum(c->tmp.p, tb, keep, kept_id, (int)n, c->stream));
-    c->stats.kernel_launches += 2;
-  }
-  // n_kept = kept_id[n-1] + keep[n-1]
-  CU_TRY(c, cudaMemcpyAsync(hs + 62, kept_id + (n - 1), 4, cudaMemcpyDeviceToHost, c->stream));
-  CU_TRY(c, cudaMemcpyAsync(hs + 63, keep + (n - 1), 4, cudaMemcpyDeviceToHost, c->stream));
-  CU_TRY(c, cudaMemcpyAsync(hs + 61, sc + 61, 4, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(hs + 61, sc + 61, 8, cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(c, cudaStreamSynchronize(c->stream));
-  const u32 n_kept = hs[62] + hs[63];
+  const u32 n_kept = hs[62];
   c->stats.rg_segments = hs[61];
+  ENSURE(c, c->out_b, ((size_t)n_kept + 1) * 4 * 3 + (size_t)n_kept * 16 + 64);
+  u32* ksize = c->out_b.as<u32>();
+  u32* kstart = ksize + (n_kept + 1);
+  u32* sid = kstart + (n_kept + 1);
+  float4* centroid = (float4*)(((uintptr_t)(sid + (n_kept + 1)) + 15) & ~(uintptr_t)15);
+  if (n_kept) {
+    u32* kept_vertex_sorted = c->vals_alt.as<u32>();  // root[] is no longer needed
+    size_t tb = 0;
+    CU_TRY(c, cub::DeviceRadixSort::SortPairs(nullptr, tb, kept_key, kept_key_sorted, kept_vertex, kept_vertex_sorted,
+                                              (int)n_kept, 0, 64, c->stream));
+    ENSURE(c, c->tmp, tb);
+    CU_TRY(c, cub::DeviceRadixSort::SortPairs(c->tmp.p, tb, kept_key, kept_key_sorted, kept_vertex,
+                                              kept_vertex_sorted, (int)n_kept, 0, 64, c->stream));
+    c->stats.kernel_launches += 2;
+    LAUNCH(c, rg_kept_ids_kernel, div_up(n_kept, 256), 256, 0, kept_vertex_sorted, size_at_seed, n_kept, kept_id,
+           ksize);
+    CHECK_LAUNCH(c);
+  }
   // point labels (original order) + member lists
   ENSURE(c, c->out_a, (size_t)n * 4);
   int* point_label = c->out_a.as<int>();
@@ -580,13 +594,7 @@ int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p) {
     CU_TRY(c, cub::DeviceRadixSort::SortPairs(c->tmp.p, tb, mkeys, mkeys_sorted, mvals, members, (int)n, 0, kbits,
                                               c->stream));
     c->stats.kernel_launches += 1 + (kbits + 7) / 8;
-    // kept cluster sizes / starts
-    ENSURE(c, c->out_b, ((size_t)n_kept + 1) * 4 * 3 + (size_t)n_kept * 16 + 64);
-    u32* ksize = c->out_b.as<u32>();
-    u32* kstart = ksize + (n_kept + 1);
-    u32* sid = kstart + (n_kept + 1);
-    float4* centroid = (float4*)(((uintptr_t)(sid + (n_kept + 1)) + 15) & ~(uintptr_t)15);
-    LAUNCH(c, rg_kept_sizes_kernel, div_up(n, 256), 256, 0, size_by_rank, keep, kept_id, n, ksize);
+    // kept cluster starts
     size_t tb2 = 0;
     CU_TRY(c, cub::DeviceScan::ExclusiveSum(nullptr, tb2, ksize, kstart, (int)n_kept, c->stream));
     ENSURE(c, c->tmp, tb2);
