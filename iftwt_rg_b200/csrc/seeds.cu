@@ -274,20 +274,37 @@ __global__ void rg_flatten_kernel(u32* __restrict__ parent, const float4* __rest
   if ((int)(threadIdx.x & 31) == __ffs(grp) - 1 && mn < *(volatile u64*)&L[r])
     atomicMin((unsigned long long*)&L[r], (unsigned long long)mn);
 }
-// arcs to root space
-__global__ void rg_arcs_to_roots_kernel(const u32* __restrict__ root, u32 m, u32* __restrict__ arc_u,
-                                        u32* __restrict__ arc_v) {
+// arcs to root space; only the arcs that join two DIFFERENT components matter to the sweeps
+// (inside a wall or a floor nearly every one-way arc stays within its component), so those are
+// appended to a compact list (out_count) and the sweeps read that list alone
+__global__ void rg_arcs_to_roots_kernel(const u32* __restrict__ root, u32 m, const u32* __restrict__ arc_u,
+                                        const u32* __restrict__ arc_v, u32* __restrict__ out_u,
+                                        u32* __restrict__ out_v, u32* __restrict__ out_count) {
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m) return;
-  arc_u[i] = root[arc_u[i]];
-  arc_v[i] = root[arc_v[i]];
+  u32 ru = 0, rv = 0;
+  if (i < m) {
+    ru = root[arc_u[i]];
+    rv = root[arc_v[i]];
+  }
+  const bool keep = ru != rv;
+  const unsigned mk = __ballot_sync(0xffffffffu, keep);
+  if (!mk) return;
+  const int lane = threadIdx.x & 31, leader = __ffs(mk) - 1;
+  u32 base = 0;
+  if (lane == leader) base = atomicAdd(out_count, (u32)__popc(mk));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (keep) {
+    const u32 pos = base + (u32)__popc(mk & ((1u << lane) - 1u));
+    out_u[pos] = ru;
+    out_v[pos] = rv;
+  }
 }
-__global__ void rg_sweep_kernel(const u32* __restrict__ arc_u, const u32* __restrict__ arc_v, u32 m,
-                                u64* __restrict__ L, u32* __restrict__ changed) {
+// m is read on the device: the grid is sized for the uncompacted list
+__global__ void rg_sweep_kernel(const u32* __restrict__ arc_u, const u32* __restrict__ arc_v,
+                                const u32* __restrict__ m_ptr, u64* __restrict__ L, u32* __restrict__ changed) {
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m) return;
+  if (i >= *m_ptr) return;
   u32 ru = arc_u[i], rv = arc_v[i];
-  if (ru == rv) return;
   u64 a = L[ru];
   if (a < L[rv]) {
     atomicMin((unsigned long long*)&L[rv], (unsigned long long)a);
@@ -523,17 +540,34 @@ int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p) {
   const u32 n_oneway = hs[56];
   u64 sweeps = 0;
   if (n_oneway) {
-    LAUNCH(c, rg_arcs_to_roots_kernel, div_up(n_oneway, 256), 256, 0, root, n_oneway, arc_u, arc_v);
+    // the compact list goes behind the full one when it fits (it does unless more than half of
+    // all arcs are one-way and smooth), else to the sort scratch
+    u32* d_m = sc + 57;
+    u32 *cu, *cv;
+    if ((size_t)n_oneway * 2 <= ne + 1) {
+      cu = arc_u + n_oneway;
+      cv = arc_v + n_oneway;
+    } else {
+      ENSURE(c, c->keys, (size_t)n_oneway * 4);
+      ENSURE(c, c->keys_alt, (size_t)n_oneway * 4);
+      cu = c->keys.as<u32>();
+      cv = c->keys_alt.as<u32>();
+    }
+    CU_TRY(c, cudaMemsetAsync(d_m, 0, 4, c->stream));
+    LAUNCH(c, rg_arcs_to_roots_kernel, div_up(n_oneway, 256), 256, 0, root, n_oneway, arc_u, arc_v, cu, cv, d_m);
+    CU_TRY(c, cudaMemcpyAsync(hs + 57, d_m, 4, cudaMemcpyDeviceToHost, c->stream));
     u32* d_changed = sc + 60;
+    u32 grid_arcs = n_oneway;  // until the compact count has come back with the first sync
     while (true) {
       CU_TRY(c, cudaMemsetAsync(d_changed, 0, 4, c->stream));
       for (int b = 0; b < 4; ++b) {
-        LAUNCH(c, rg_sweep_kernel, div_up(n_oneway, 256), 256, 0, arc_u, arc_v, n_oneway, L, d_changed);
+        LAUNCH(c, rg_sweep_kernel, div_up(grid_arcs ? grid_arcs : 1, 256), 256, 0, cu, cv, d_m, L, d_changed);
         ++sweeps;
       }
       CHECK_LAUNCH(c);
       CU_TRY(c, cudaMemcpyAsync(hs + 60, d_changed, 4, cudaMemcpyDeviceToHost, c->stream));
       CU_TRY(c, cudaStreamSynchronize(c->stream));
+      grid_arcs = hs[57];
       if (hs[60] == 0) break;
       if (sweeps > 400000) return ctx_fail(c, IFTWT_ERR_CUDA, "region growing did not converge");
     }
