@@ -53,10 +53,6 @@ __device__ __forceinline__ bool smooth_pass(const float4 nu, const float4 nv, fl
 __device__ __forceinline__ u64 rg_key(const float4* __restrict__ nrm, const float4* __restrict__ spts, u32 v) {
   return ((u64)__float_as_uint(nrm[v].w) << 32) | (u64)__float_as_uint(spts[v].w);
 }
-__global__ void iota_kernel(u32* __restrict__ a, u32 n) {
-  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) a[i] = i;
-}
 // Region-growing arcs in two kernels.
 //
 // rg_classify_kernel — one warp per tile of 32 consecutive (Morton-adjacent) vertices, one lane
@@ -92,7 +88,7 @@ __global__ void __launch_bounds__(RGA_WARPS * 32, 4)
 rg_classify_kernel(const u32* __restrict__ nbr, const float* __restrict__ nd2, const u64* __restrict__ kth,
                    const float4* __restrict__ spts, u64* __restrict__ ow_mask, const float4* __restrict__ nrm, u32 n,
                    int k, float cos_thr, u64* __restrict__ hook_mask, u64* __restrict__ list_mask,
-                   u32* __restrict__ rdeg, unsigned long long* __restrict__ n_fwd) {
+                   u32* __restrict__ rdeg, unsigned long long* __restrict__ n_fwd, u32* __restrict__ parent) {
   extern __shared__ __align__(16) unsigned char rga_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int fs = rga_flag_stride(k);
@@ -174,6 +170,15 @@ rg_classify_kernel(const u32* __restrict__ nbr, const float* __restrict__ nd2, c
       if ((f & 14u) == 12u) hk |= 1ull << j;  // smooth mutual, v < u: the twin arc is mutual and smooth
     }                                         // too; one of the pair hooks
     if (FUSED) ow_mask[u] = ow;
+    // ECL-CC's initialisation: u starts under its nearest hook neighbour (a smaller id, so the
+    // links stay acyclic) — one plain store instead of two finds and a CAS, and the hook kernel
+    // starts from a forest instead of n singletons
+    u32 par = u;
+    if (hk) {
+      par = nbr[(size_t)u * k + (__ffsll((long long)hk) - 1)];
+      hk &= hk - 1;
+    }
+    parent[u] = par;
     hook_mask[u] = hk;
     list_mask[u] = ls;
   }
@@ -448,12 +453,11 @@ int fused_graph_rg_run(iftwt_ctx* c, const iftwt_rg_params* p) {
   ENSURE(c, c->rg_masks, (size_t)n * 16);
   u64* hook_mask = c->rg_masks.as<u64>();
   u64* list_mask = hook_mask + n;
-  LAUNCH(c, iota_kernel, div_up(n, 256), 256, 0, c->rg_parent.as<u32>(), n);
   CU_TRY(c, cudaFuncSetAttribute(rg_classify_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)rga_smem_bytes(k)));
   LAUNCH(c, rg_classify_kernel<true>, div_up(n, RGA_WARPS * 32), RGA_WARPS * 32, rga_smem_bytes(k), c->nbr.as<u32>(),
          c->nd2.as<float>(), c->kth.as<u64>(), c->spts.as<float4>(), c->ow_mask.as<u64>(), c->nrm.as<float4>(), n, k,
-         cos_thr, hook_mask, list_mask, c->g_deg.as<u32>(), d_nfwd);
+         cos_thr, hook_mask, list_mask, c->g_deg.as<u32>(), d_nfwd, c->rg_parent.as<u32>());
   LAUNCH(c, rg_hook_kernel, div_up(n, 256), 256, 0, c->nbr.as<u32>(), hook_mask, list_mask, n, k,
          c->rg_parent.as<u32>(), d_cnt, arc_u, arc_u + (ne + 1));
   CHECK_LAUNCH(c);
@@ -515,7 +519,6 @@ int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p) {
     ENSURE(c, c->rg_aux2, (ne + 1) * 8);
     arc_u = c->rg_aux2.as<u32>();
     arc_v = arc_u + (ne + 1);
-    LAUNCH(c, iota_kernel, div_up(n, 256), 256, 0, parent, n);
     if (c->mask_k != c->knn_k) TRY(knn_mutual_run(c, false));
     ENSURE(c, c->rg_masks, (size_t)n * 16);
     u64* hook_mask = c->rg_masks.as<u64>();
@@ -524,7 +527,7 @@ int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p) {
                                    (int)rga_smem_bytes(k)));
     LAUNCH(c, rg_classify_kernel<false>, div_up(n, RGA_WARPS * 32), RGA_WARPS * 32, rga_smem_bytes(k),
            c->nbr.as<u32>(), (const float*)nullptr, (const u64*)nullptr, (const float4*)nullptr, c->ow_mask.as<u64>(),
-           nrm, n, k, cos_thr, hook_mask, list_mask, (u32*)nullptr, (unsigned long long*)nullptr);
+           nrm, n, k, cos_thr, hook_mask, list_mask, (u32*)nullptr, (unsigned long long*)nullptr, parent);
     LAUNCH(c, rg_hook_kernel, div_up(n, 256), 256, 0, c->nbr.as<u32>(), hook_mask, list_mask, n, k, parent, d_cnt,
            arc_u, arc_v);
     CHECK_LAUNCH(c);
