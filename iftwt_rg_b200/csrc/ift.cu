@@ -177,7 +177,10 @@ __device__ __forceinline__ void ift_visit(u64* __restrict__ node, u32 level, u32
 // 1.4 -> 2.5 ms) and the IFT itself (6.2 -> 7.9 ms); a w16 pre-gather that skips the node word of
 // closed neighbours (one more link in the chain: 6.2 -> 6.5 ms); runs of consecutive small levels
 // in one cooperative launch with a grid barrier between levels and ld.cg node reads (6.34 vs
-// 6.23 ms: a barrier over 1184 resident blocks is no cheaper than a launch boundary).
+// 6.23 ms: a barrier over 1184 resident blocks is no cheaper than a launch boundary); a pre-pass
+// that marks, per vertex, the forward neighbours that are not heavier, so that the level kernels
+// skip the arcs to still-closed neighbours (half of the forward visits) — the pre-pass and the
+// extra mask load cost more than the skipped visits saved (6.2 -> 7.1 ms).
 template <int G>
 __global__ void __launch_bounds__(256, 8)  // 32 registers: 2048 chains in flight per SM
 ift_level_kernel(const u32* __restrict__ byw, u32 seg_begin, u32 seg_len, u32 level, u32 open_blocks,
