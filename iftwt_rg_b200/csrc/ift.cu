@@ -181,11 +181,13 @@ __device__ __forceinline__ void ift_visit(u64* __restrict__ node, u32 level, u32
 // that marks, per vertex, the forward neighbours that are not heavier, so that the level kernels
 // skip the arcs to still-closed neighbours (half of the forward visits) — the pre-pass and the
 // extra mask load cost more than the skipped visits saved (6.2 -> 7.1 ms).
+#define IFT_PEND 6
 template <int G>
 __global__ void __launch_bounds__(256, 8)  // 32 registers: 2048 chains in flight per SM
 ift_level_kernel(const u32* __restrict__ byw, u32 seg_begin, u32 seg_len, u32 level, u32 open_blocks,
                  u32 prev_begin, u32 prev_len, const u32* __restrict__ fwd, int k,
                  const u32* __restrict__ roff, const u32* __restrict__ radj, u64* __restrict__ node) {
+  __shared__ u32 s_pend[G == 32 ? 1 : 256 * IFT_PEND];
   if (blockIdx.x >= open_blocks) {
     const u32 i = (blockIdx.x - open_blocks) * blockDim.x + threadIdx.x;
     if (i >= prev_len) return;
@@ -229,9 +231,41 @@ ift_level_kernel(const u32* __restrict__ byw, u32 seg_begin, u32 seg_len, u32 le
         if (u1 != 0xFFFFFFFFu) ift_visit(node, level, rt, xt, u1, x1, lmin);
       }
     } else {
-      for (u32 i = gl; i < na; i += G) {
-        const u32 u = i < (u32)k ? row[i] : radj[b + i - k];
-        if (u != 0xFFFFFFFFu && u != t) ift_visit(node, level, rt, xt, u, node[u], lmin);
+      // Several vertices share a warp here, and a visit that needs the union-find (a chase, a CAS)
+      // would stall all of them: with ~3 same-level neighbours per vertex some lane of the warp
+      // needs one in nearly every round.  So the pass over the arcs only gathers — conquered
+      // neighbours give their label, closed ones are dropped, two rounds of loads in flight — and
+      // the few neighbours that need the union-find are parked and worked off afterwards, when
+      // every busy lane is doing that same kind of work.
+      u32* pend = s_pend + threadIdx.x;  // slot q of this thread at pend[256 q]
+      int np = 0;
+      for (u32 i = gl; i < na; i += 2 * G) {
+        const u32 i1 = i + G;
+        u32 u0 = i < (u32)k ? row[i] : radj[b + i - k];
+        u32 u1 = i1 < na ? (i1 < (u32)k ? row[i1] : radj[b + i1 - k]) : 0xFFFFFFFFu;
+        if (u0 == t) u0 = 0xFFFFFFFFu;
+        if (u1 == t) u1 = 0xFFFFFFFFu;
+        const u64 x0 = u0 != 0xFFFFFFFFu ? node[u0] : ~0ull;
+        const u64 x1 = u1 != 0xFFFFFFFFu ? node[u1] : ~0ull;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const u32 u = q ? u1 : u0;
+          const u64 x = q ? x1 : x0;
+          const u32 h = NODE_HI(x);
+          if (h != 0 && h < level + 2u) {
+            lmin = min(lmin, NODE_LO(x));  // conquered at an earlier level
+          } else if (h >= NODE_UNCONQ && h - NODE_UNCONQ > level) {
+            // closed at this level (or no neighbour: the filler word)
+          } else if (np < IFT_PEND) {
+            pend[256 * np++] = u;
+          } else {
+            ift_visit(node, level, rt, xt, u, x, lmin);
+          }
+        }
+      }
+      for (int q = 0; q < np; ++q) {
+        const u32 u = pend[256 * q];
+        ift_visit(node, level, rt, xt, u, node[u], lmin);
       }
     }
   }
