@@ -182,6 +182,7 @@ __device__ __forceinline__ void ift_visit(u64* __restrict__ node, u32 level, u32
 // skip the arcs to still-closed neighbours (half of the forward visits) — the pre-pass and the
 // extra mask load cost more than the skipped visits saved (6.2 -> 7.1 ms).
 #define IFT_PEND 6
+#define IFT_AHEAD 2  // 3 / 4 rounds ahead spill at 32 registers: 5.84 / 5.95 ms against 5.70; 4 ahead at 40 registers: 6.2 ms
 template <int G>
 __global__ void __launch_bounds__(256, 8)  // 32 registers: 2048 chains in flight per SM
 ift_level_kernel(const u32* __restrict__ byw, u32 seg_begin, u32 seg_len, u32 level, u32 open_blocks,
@@ -234,23 +235,26 @@ ift_level_kernel(const u32* __restrict__ byw, u32 seg_begin, u32 seg_len, u32 le
       // Several vertices share a warp here, and a visit that needs the union-find (a chase, a CAS)
       // would stall all of them: with ~3 same-level neighbours per vertex some lane of the warp
       // needs one in nearly every round.  So the pass over the arcs only gathers — conquered
-      // neighbours give their label, closed ones are dropped, two rounds of loads in flight — and
+      // neighbours give their label, closed ones are dropped, IFT_AHEAD rounds of loads in flight — and
       // the few neighbours that need the union-find are parked and worked off afterwards, when
       // every busy lane is doing that same kind of work.
       u32* pend = s_pend + threadIdx.x;  // slot q of this thread at pend[256 q]
       int np = 0;
-      for (u32 i = gl; i < na; i += 2 * G) {
-        const u32 i1 = i + G;
-        u32 u0 = i < (u32)k ? row[i] : radj[b + i - k];
-        u32 u1 = i1 < na ? (i1 < (u32)k ? row[i1] : radj[b + i1 - k]) : 0xFFFFFFFFu;
-        if (u0 == t) u0 = 0xFFFFFFFFu;
-        if (u1 == t) u1 = 0xFFFFFFFFu;
-        const u64 x0 = u0 != 0xFFFFFFFFu ? node[u0] : ~0ull;
-        const u64 x1 = u1 != 0xFFFFFFFFu ? node[u1] : ~0ull;
+      for (u32 i0 = gl; i0 < na; i0 += IFT_AHEAD * G) {
+        u32 uu[IFT_AHEAD];
+        u64 xx[IFT_AHEAD];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const u32 u = q ? u1 : u0;
-          const u64 x = q ? x1 : x0;
+        for (int q = 0; q < IFT_AHEAD; ++q) {
+          const u32 i = i0 + q * G;
+          uu[q] = i < na ? (i < (u32)k ? row[i] : radj[b + i - k]) : 0xFFFFFFFFu;
+          if (uu[q] == t) uu[q] = 0xFFFFFFFFu;
+        }
+#pragma unroll
+        for (int q = 0; q < IFT_AHEAD; ++q) xx[q] = uu[q] != 0xFFFFFFFFu ? node[uu[q]] : ~0ull;
+#pragma unroll
+        for (int q = 0; q < IFT_AHEAD; ++q) {
+          const u32 u = uu[q];
+          const u64 x = xx[q];
           const u32 h = NODE_HI(x);
           if (h != 0 && h < level + 2u) {
             lmin = min(lmin, NODE_LO(x));  // conquered at an earlier level
@@ -339,7 +343,7 @@ int ift_run(iftwt_ctx* c, const float* d_w_orig, const u32* d_seeds_orig, size_t
   u64 levels = 0;
   u32 prev_b = 0, prev_len = 0;
   const char* wenv = getenv("IFTWT_IFT_WAVES");
-  const double waves = wenv ? atof(wenv) : 4.0;  // swept on B200: 1 -> 7.7 ms, 2 -> 6.7, 4 -> 6.3, 8 -> 6.8, 16 -> 7.7
+  const double waves = wenv ? atof(wenv) : 3.0;  // swept on B200: 1 -> 6.1 ms, 2 -> 5.8, 3 -> 5.65, 4 -> 5.8, 6 -> 6.15, 8 -> 6.4
   for (u32 lv = 0; lv < IFTWT_MAX_COST; ++lv) {
     u32 b = seg[lv], len = seg[lv + 1] - seg[lv];
     if (len == 0) continue;
