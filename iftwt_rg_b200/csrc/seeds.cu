@@ -189,12 +189,14 @@ rg_classify_kernel(const u32* __restrict__ nbr, const float* __restrict__ nd2, c
   }
 }
 
+#define HOOK_S 8
 __global__ void __launch_bounds__(256)
 rg_hook_kernel(const u32* __restrict__ nbr, const u64* __restrict__ hook_mask, const u64* __restrict__ list_mask,
                u32 n, int k, u32* __restrict__ parent, u32* __restrict__ counter, u32* __restrict__ arc_u,
                u32* __restrict__ arc_v) {
   __shared__ u32 s_warp[8];
   __shared__ u32 s_base;
+  __shared__ u32 s_v[256 * HOOK_S];
   const u32 u = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   u64 mask = 0;
@@ -203,24 +205,43 @@ rg_hook_kernel(const u32* __restrict__ nbr, const u64* __restrict__ hook_mask, c
     u64 hk = hook_mask[u];
     mask = list_mask[u];
     u32 ru = 0xFFFFFFFFu;
+    // HOOK_S arcs at a time: first all the row entries, then all their parents — independent
+    // loads the hardware overlaps — and only then the finds and hooks, which are chains
+    u32* sv = s_v + threadIdx.x;  // slot q of this thread at sv[256 q]
     while (hk) {
-      const int j = __ffsll((long long)hk) - 1;
-      hk &= hk - 1;
-      const u32 v = row[j];
+      int m = 0;
+      u64 h2 = hk;
+#pragma unroll
+      for (int q = 0; q < HOOK_S; ++q) {
+        if (h2) {
+          const int j = __ffsll((long long)h2) - 1;
+          h2 &= h2 - 1;
+          sv[256 * q] = row[j];
+          m = q + 1;
+        }
+      }
+      hk = h2;
+#pragma unroll
+      for (int q = 0; q < HOOK_S; ++q)
+        if (q < m) sv[256 * q] = parent[sv[256 * q]];  // one step up: v itself is never needed again
       if (ru == 0xFFFFFFFFu) ru = uf_find(parent, u);
-      u32 rv = uf_find(parent, v);
-      while (ru != rv) {
-        if (ru < rv) {
-          u32 ret = atomicCAS(&parent[rv], rv, ru);
-          if (ret == rv) break;
-          rv = ret;
-        } else {
-          u32 ret = atomicCAS(&parent[ru], ru, rv);
-          if (ret == ru) {
-            ru = rv;
-            break;
+      for (int q = 0; q < m; ++q) {
+        u32 rv = sv[256 * q];
+        if (rv == ru) continue;  // v hangs directly under u's representative
+        rv = uf_find(parent, rv);
+        while (ru != rv) {
+          if (ru < rv) {
+            u32 ret = atomicCAS(&parent[rv], rv, ru);
+            if (ret == rv) break;
+            rv = ret;
+          } else {
+            u32 ret = atomicCAS(&parent[ru], ru, rv);
+            if (ret == ru) {
+              ru = rv;
+              break;
+            }
+            ru = ret;
           }
-          ru = ret;
         }
       }
     }
