@@ -135,6 +135,29 @@ int dev_ensure(iftwt_ctx* c, DevBuf& b, size_t bytes);
     (ctx)->stats.kernel_launches++;                                         \
   } while (0)
 #define CHECK_LAUNCH(ctx) CU_TRY(ctx, cudaGetLastError())
+// Programmatic dependent launch: the kernel may become resident while its predecessor in the
+// stream is still running; everything it does before pdl_wait() must not depend on it.
+#define LAUNCH_PDL(ctx, kernel, grid, block, smem, ...)                               \
+  do {                                                                                \
+    cudaLaunchConfig_t cfg_ = {};                                                     \
+    cfg_.gridDim = dim3(grid);                                                        \
+    cfg_.blockDim = dim3(block);                                                      \
+    cfg_.dynamicSmemBytes = (smem);                                                   \
+    cfg_.stream = (ctx)->stream;                                                      \
+    cudaLaunchAttribute at_[1];                                                       \
+    at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                   \
+    at_[0].val.programmaticStreamSerializationAllowed = 1;                            \
+    cfg_.attrs = at_;                                                                 \
+    cfg_.numAttrs = 1;                                                                \
+    cudaLaunchKernelEx(&cfg_, kernel, __VA_ARGS__);                                   \
+    (ctx)->stats.kernel_launches++;                                                   \
+  } while (0)
+#ifdef __CUDACC__
+// lets the next kernel of the stream start its independent prologue
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+// returns when every earlier kernel of the stream has completed and its writes are visible
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
 
 struct StageTimer {
   iftwt_ctx* c;
