@@ -228,7 +228,14 @@ ift_level_kernel(const u32* __restrict__ byw, u32 seg_begin, u32 seg_len, u32 le
     }
   }
   pdl_wait();
+  u64 q0 = 0, q1 = 0;  // G == 32: the words of the first two neighbours, in flight with node[t]
   if (active) {
+    if (G == 32) {
+      if (p0 == t) p0 = 0xFFFFFFFFu;
+      if (p1 == t) p1 = 0xFFFFFFFFu;
+      if (p0 != 0xFFFFFFFFu) q0 = node[p0];
+      if (p1 != 0xFFFFFFFFu) q1 = node[p1];
+    }
     rt = t;
     xt = node_find(node, rt, node[t]);       // t may already hang under a same-level neighbour
     work = NODE_HI(xt) >= level + 2u;        // a seed is conquered from the start
@@ -241,14 +248,15 @@ ift_level_kernel(const u32* __restrict__ byw, u32 seg_begin, u32 seg_len, u32 le
       for (u32 i = gl; i < na; i += 2 * G) {
         const u32 i1 = i + G;
         u32 u0 = p0, u1 = p1;
+        u64 x0 = q0, x1 = q1;
         if (i != (u32)gl) {
           u0 = i < (u32)k ? row[i] : radj[b + i - k];
           u1 = i1 < na ? (i1 < (u32)k ? row[i1] : radj[b + i1 - k]) : 0xFFFFFFFFu;
+          if (u0 == t) u0 = 0xFFFFFFFFu;
+          if (u1 == t) u1 = 0xFFFFFFFFu;
+          x0 = u0 != 0xFFFFFFFFu ? node[u0] : 0ull;
+          x1 = u1 != 0xFFFFFFFFu ? node[u1] : 0ull;
         }
-        if (u0 == t) u0 = 0xFFFFFFFFu;
-        if (u1 == t) u1 = 0xFFFFFFFFu;
-        const u64 x0 = u0 != 0xFFFFFFFFu ? node[u0] : 0ull;
-        const u64 x1 = u1 != 0xFFFFFFFFu ? node[u1] : 0ull;
         if (u0 != 0xFFFFFFFFu) ift_visit(node, level, rt, xt, u0, x0, lmin);
         if (u1 != 0xFFFFFFFFu) ift_visit(node, level, rt, xt, u1, x1, lmin);
       }
