@@ -355,9 +355,31 @@ def main():
                     "peak_source": which, "algorithmic_bytes_per_launch": alg_bytes,
                     "avg_launch_ms": knn_ms}
         nrm_ms = stage_ms.get("normals", 0.0)
+        # IFT: algorithmic bytes 20 V + 12 E-> over the whole stage, and the global-atomic
+        # rate — atomics counted by ncu at L2 (atomicMin offers + atomicCAS hooks of all level kernels of
+        # one run, profiles/kernel_traffic.json) over the stage time measured in THIS run
+        ift_ms = stage_ms.get("ift", 0.0)
+        ift = None
+        if ift_ms > 0:
+            ift_bytes = 20 * n + 12 * int(stats["n_arcs"])
+            ift = {"ms": ift_ms, "levels": int(stats["ift_levels"]), "algorithmic_bytes": ift_bytes,
+                   "achieved_gbs": ift_bytes / (ift_ms * 1e-3) / 1e9,
+                   "frac_of_hbm": ift_bytes / (ift_ms * 1e-3) / 1e9 / peak if peak else None,
+                   "bound": "latency of dependent gathers / atomics, not bandwidth"}
+            try:
+                ta = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json"))).get(args.workload + "_ift")
+                if ta and n == n_default and k == k_default:
+                    atoms = int(ta["l2_atomic_alu_requests"]) + int(ta["l2_atomic_cas_requests"])
+                    ift["atomics_per_run"] = atoms
+                    ift["atomics_per_s"] = atoms / (ift_ms * 1e-3)
+                    ift["atomics_source"] = ta["source"]
+            except Exception:
+                pass
         extra = {
             "stage_ms": stage_ms,
             "normals_gbs": ((32 + 4 * k) * n) / (nrm_ms * 1e-3) / 1e9 if nrm_ms > 0 else None,
+            "normals_frac_of_hbm": ((32 + 4 * k) * n) / (nrm_ms * 1e-3) / 1e9 / peak if nrm_ms > 0 and peak else None,
+            "ift": ift,
             "stats": {kk: stats[kk] for kk in ("n_cells", "cell_size", "knn_fallback", "n_arcs", "rg_segments",
                                                 "rg_sweeps", "n_seeds", "ift_levels")},
         }
