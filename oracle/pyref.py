@@ -1,0 +1,68 @@
+"""ctypes wrapper of oracle/_ref/libref_ift.so — the REFERENCE's own IFT (ift.hpp +
+globals.hpp compiled unmodified from /root/reference against oracle/shim, driver
+oracle/ref_ift_driver.cpp).
+
+TEST INFRASTRUCTURE, same rules as pyoracle: tests/ and tools/ only.  The library is
+built in the development container (where /root/reference exists) and travels to the GPU
+box prebuilt; nothing here reads /root/reference at run time.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "_ref", "libref_ift.so")
+REFERENCE = os.environ.get("IFTWT_REFERENCE", "/root/reference")
+
+
+def build(force: bool = False) -> str | None:
+    """Builds _ref/libref_ift.so when the reference sources are present; None otherwise."""
+    if not os.path.exists(os.path.join(REFERENCE, "ift.hpp")):
+        return _LIB if os.path.exists(_LIB) else None
+    if force and os.path.exists(_LIB):
+        os.remove(_LIB)
+    subprocess.check_call(["make", "-C", _HERE, "-s", "ref", f"REFERENCE={REFERENCE}"])
+    return _LIB
+
+
+def available() -> bool:
+    return os.path.exists(_LIB)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(_LIB)
+        _lib.ref_ift_run.restype = C.c_int64
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def ift(pts, off, adj, seeds_xyz):
+    """IFT_PCD(Graph&, Cloud::Ptr seeds) of ift.hpp:31-37 on the graph (pts, off, adj).
+    pts: n x {x, y, z, intensity}; seeds_xyz: ns x 3.  Returns cost[n], root[n] (vertex index of the
+    conquering seed, self when unreached) and the reference's `mst` map as (a, b, weight) rows."""
+    pts = np.ascontiguousarray(pts, np.float32)
+    off = np.ascontiguousarray(off, np.uint32)
+    adj = np.ascontiguousarray(adj, np.uint32)
+    seeds_xyz = np.ascontiguousarray(seeds_xyz, np.float32).reshape(-1, 3)
+    n = pts.shape[0]
+    cost = np.empty(n, np.uint32)
+    root = np.empty(n, np.uint32)
+    cap = max(1, seeds_xyz.shape[0])
+    a = np.empty(cap, np.uint32)
+    b = np.empty(cap, np.uint32)
+    w = np.empty(cap, np.float64)
+    m = int(lib().ref_ift_run(_p(pts), C.c_int64(n), _p(off), _p(adj), _p(seeds_xyz), C.c_int64(seeds_xyz.shape[0]),
+                              _p(cost), _p(root), _p(a), _p(b), _p(w), C.c_int64(cap)))
+    return cost, root, a[:m], b[:m], w[:m]

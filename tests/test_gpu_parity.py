@@ -285,3 +285,29 @@ def test_segment_with_gradient_weights(ctx):
     grad = orc.morph(roff, radj, pts[:, 3], orc.MORPH_GRADIENT)
     rcost, rlabel = orc.ift(roff, radj, grad, rseeds, orc.POLICY_C)
     assert ns == kept and np.array_equal(cost, rcost) and np.array_equal(label, rlabel)
+
+
+@pytest.mark.parametrize("name", ["knn8_3k", "knn16_6k"])
+def test_ift_against_the_reference_own_code(ctx, name):
+    """GPU vs the REFERENCE's IFT_PCD (ift.hpp compiled unmodified, outputs committed as
+    tests/golden/ref_ift_*.npz by tools/make_ref_ift_golden.py): the graph the GPU builds is the
+    fixture's, costs are bit-exact, labels are an admissible tie-break; disagreements are counted."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", f"ref_ift_{name}.npz"))
+    pts, k = z["pts"], int(z["k"])
+    ctx.set_cloud(pts)
+    off, adj = ctx.knn_graph(k)
+    assert np.array_equal(off, z["off"]) and np.array_equal(adj, z["adj"])
+    q = np.zeros((len(z["seeds_xyz"]), 4), np.float32)
+    q[:, :3] = z["seeds_xyz"]
+    sidx, _ = ctx.knn_query(q, 1)                     # the seed snap of ift.hpp:135
+    seeds = sidx[:, 0].astype(np.int32)
+    cost, label = ctx.ift(None, seeds)
+    assert np.array_equal(cost, z["ref_cost"])
+    assert orc.ift_audit(off, adj, pts[:, 3], seeds, cost, label) == 0
+    seed_set = np.zeros(len(pts), bool)
+    seed_set[seeds] = True
+    assert np.array_equal(label[seed_set], np.flatnonzero(seed_set).astype(np.uint32))
+    assert np.array_equal(label[seed_set], z["ref_root"][seed_set])
+    diff = int(np.count_nonzero(label != z["ref_root"]))
+    print(f"{name}: tie-only label disagreements GPU (policy C) vs the reference's own run: {diff}/{len(pts)}")

@@ -1,0 +1,112 @@
+"""The oracle against the REFERENCE's own IFT code.
+
+oracle/_ref/libref_ift.so is ift.hpp + globals.hpp of /root/reference compiled UNMODIFIED
+(oracle/ref_ift_driver.cpp) against the API stand-ins of oracle/shim; its outputs on five
+graphs are committed as tests/golden/ref_ift_*.npz (tools/make_ref_ift_golden.py).  These tests
+pin, on those fixtures and live when the library is present:
+
+* the oracle's literal restatement (orc_ift_literal_mst: cost, root label and the `mst` map of
+  ift.hpp:207-243) == the reference, bit for bit;
+* the costs of the product policies C (min seed — the GPU contract) and R (first offer) == the
+  reference's costs;
+* the reference's own labels, and the labels of both policies, pass the tie-admissibility audit,
+  and the label disagreements are counted (ties only by construction of the audit).
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as orc
+from oracle import pyref
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_ift_*.npz")))
+NAMES = [os.path.basename(p)[len("ref_ift_"):-4] for p in GOLDEN]
+
+
+def load(path):
+    z = np.load(path)
+    d = {k: z[k] for k in z.files}
+    # IFT_PCD snaps every seed point to its nearest graph vertex (ift.hpp:135)
+    q = np.zeros((len(d["seeds_xyz"]), 4), np.float32)
+    q[:, :3] = d["seeds_xyz"]
+    idx, _ = orc.knn_query(d["pts"], q, 1, brute=True)
+    d["seeds"] = idx[:, 0].astype(np.int32)
+    return d
+
+
+def test_fixtures_exist():
+    assert len(GOLDEN) >= 5
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=NAMES)
+def test_oracle_literal_equals_reference(path):
+    d = load(path)
+    cost, label, a, b, w = orc.ift_literal_mst(d["off"], d["adj"], d["pts"][:, 3], d["seeds"])
+    assert np.array_equal(cost, d["ref_cost"])
+    assert np.array_equal(label, d["ref_root"])
+    assert np.array_equal(a, d["ref_mst_a"]) and np.array_equal(b, d["ref_mst_b"])
+    assert np.array_equal(w, d["ref_mst_w"])  # doubles, bit for bit
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=NAMES)
+def test_policy_costs_equal_reference_and_labels_are_admissible(path):
+    d = load(path)
+    off, adj, w, seeds = d["off"], d["adj"], d["pts"][:, 3], d["seeds"]
+    n = len(w)
+    # the reference's own output is a valid tie-break of its rule
+    assert orc.ift_audit(off, adj, w, seeds, d["ref_cost"], d["ref_root"]) == 0
+    for policy, tag in ((orc.POLICY_C, "C min-seed"), (orc.POLICY_R, "R first-offer")):
+        cost, label = orc.ift(off, adj, w, seeds, policy)
+        assert np.array_equal(cost, d["ref_cost"]), tag
+        assert orc.ift_audit(off, adj, w, seeds, cost, label) == 0, tag
+        unreached = cost >= 500
+        assert np.array_equal(label[unreached], np.arange(n, dtype=np.uint32)[unreached])
+        diff = int(np.count_nonzero(label != d["ref_root"]))
+        print(f"{os.path.basename(path)}: policy {tag}: tie-only label disagreements vs the reference: {diff}/{n}")
+
+
+needs_ref = pytest.mark.skipif(not (pyref.available() or os.path.exists(os.path.join(pyref.REFERENCE, "ift.hpp"))),
+                               reason="oracle/_ref/libref_ift.so is built where /root/reference exists")
+
+
+@needs_ref
+@pytest.mark.parametrize("path", GOLDEN, ids=NAMES)
+def test_reference_live_equals_fixture(path):
+    pyref.build()
+    d = load(path)
+    cost, root, a, b, w = pyref.ift(d["pts"], d["off"], d["adj"], d["seeds_xyz"])
+    assert np.array_equal(cost, d["ref_cost"]) and np.array_equal(root, d["ref_root"])
+    assert np.array_equal(a, d["ref_mst_a"]) and np.array_equal(b, d["ref_mst_b"]) and np.array_equal(w, d["ref_mst_w"])
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_reference_live_random_graphs(seed):
+    """Random sparse graphs with few intensity values (ties everywhere), random seeds."""
+    pyref.build()
+    rng = np.random.default_rng(seed)
+    n = 400
+    pts = np.zeros((n, 4), np.float32)
+    pts[:, :3] = rng.random((n, 3), dtype=np.float32)
+    pts[:, 3] = rng.integers(0, 4 + 3 * seed, n)
+    nb = [set() for _ in range(n)]
+    for _ in range(3 * n):
+        a, b = rng.integers(0, n, 2)
+        if a != b:
+            nb[a].add(int(b))
+            nb[b].add(int(a))
+    off = np.zeros(n + 1, np.uint32)
+    adj = []
+    for i in range(n):
+        adj += sorted(nb[i])
+        off[i + 1] = len(adj)
+    adj = np.array(adj, np.uint32)
+    seeds = np.sort(rng.choice(n, 6, replace=False)).astype(np.int32)
+    cost, root, a, b, w = pyref.ift(pts, off, adj, pts[seeds, :3])
+    ocost, olabel, oa, ob, ow = orc.ift_literal_mst(off, adj, pts[:, 3], seeds)
+    assert np.array_equal(cost, ocost) and np.array_equal(root, olabel)
+    assert np.array_equal(a, oa) and np.array_equal(b, ob) and np.array_equal(w, ow)
+    ccost, _ = orc.ift(off, adj, pts[:, 3], seeds, orc.POLICY_C)
+    assert np.array_equal(cost, ccost)
