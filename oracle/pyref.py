@@ -66,3 +66,83 @@ def ift(pts, off, adj, seeds_xyz):
     m = int(lib().ref_ift_run(_p(pts), C.c_int64(n), _p(off), _p(adj), _p(seeds_xyz), C.c_int64(seeds_xyz.shape[0]),
                               _p(cost), _p(root), _p(a), _p(b), _p(w), C.c_int64(cap)))
     return cost, root, a[:m], b[:m], w[:m]
+
+
+# ---- the reference's own Graph (graph.hpp) + IFT_PCD on it: oracle/_ref/libref_graph.so ----
+_LIBG = os.path.join(_HERE, "_ref", "libref_graph.so")
+_libg = None
+
+
+def graph_available() -> bool:
+    return os.path.exists(_LIBG)
+
+
+def libg():
+    global _libg
+    if _libg is None:
+        _libg = C.CDLL(_LIBG)
+        _libg.ref_graph_create.restype = C.c_void_p
+        _libg.ref_graph_resolution.restype = C.c_double
+        for f in ("ref_graph_cloud", "ref_graph_csr", "ref_graph_regmin", "ref_graph_ift"):
+            getattr(_libg, f).restype = C.c_int64
+    return _libg
+
+
+class RefGraph:
+    """`Graph gg(cloud, overlap)` of graph.hpp:43-50 — vertices are numbered in the graph's own
+    iteration order (ascending voxel Morton key with the shim's octree)."""
+
+    def __init__(self, pts, overlap: float = 1.01):
+        pts = np.ascontiguousarray(pts, np.float32)
+        self._h = C.c_void_p(libg().ref_graph_create(_p(pts), C.c_int64(pts.shape[0]), C.c_double(overlap)))
+        self.n = int(libg().ref_graph_cloud(self._h, None))
+
+    def close(self):
+        if self._h:
+            libg().ref_graph_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def resolution(self) -> float:
+        return float(libg().ref_graph_resolution(self._h))
+
+    def cloud(self):
+        out = np.empty((self.n, 4), np.float32)
+        libg().ref_graph_cloud(self._h, _p(out))
+        return out
+
+    def csr(self):
+        off = np.empty(self.n + 1, np.uint32)
+        loops = C.c_int64(0)
+        m = int(libg().ref_graph_csr(self._h, _p(off), None, C.byref(loops)))
+        adj = np.empty(max(m, 1), np.uint32)
+        libg().ref_graph_csr(self._h, _p(off), _p(adj), C.byref(loops))
+        return off, adj[:m], int(loops.value)
+
+    def morph(self, op: int):
+        out = np.empty(self.n, np.float32)
+        rc = libg().ref_graph_morph(self._h, C.c_int(op), _p(out))
+        assert rc == 0
+        return out
+
+    def regmin(self):
+        idx = np.empty(self.n, np.int32)
+        m = int(libg().ref_graph_regmin(self._h, _p(idx)))
+        return idx[:m].copy()
+
+    def ift(self, seeds_xyz):
+        seeds_xyz = np.ascontiguousarray(seeds_xyz, np.float32).reshape(-1, 3)
+        cost = np.empty(self.n, np.uint32)
+        root = np.empty(self.n, np.uint32)
+        cap = max(1, seeds_xyz.shape[0])
+        a = np.empty(cap, np.uint32)
+        b = np.empty(cap, np.uint32)
+        w = np.empty(cap, np.float64)
+        m = int(libg().ref_graph_ift(self._h, _p(seeds_xyz), C.c_int64(seeds_xyz.shape[0]), _p(cost), _p(root),
+                                     _p(a), _p(b), _p(w), C.c_int64(cap)))
+        return cost, root, a[:m], b[:m], w[:m]

@@ -230,6 +230,27 @@ IFTWT_SHIM_TP std::size_t num_edges(const IFTWT_SHIM_AL& g) { return g.edge_list
 #undef IFTWT_SHIM_TP
 }  // namespace boost
 
+// <boost/graph/copy.hpp>, as called at graph.hpp:315-317: vertices in the source's iteration order,
+// edges in its edge-list order; the vertex-index map only serves Boost's internal bookkeeping
+namespace boost {
+template <class M>
+struct shim_assoc_map {
+  M* m;
+};
+template <class M>
+shim_assoc_map<M> make_assoc_property_map(M& m) { return shim_assoc_map<M>{&m}; }
+template <class P>
+struct shim_named_param {
+  P p;
+};
+template <class P>
+shim_named_param<P> vertex_index_map(const P& p) { return shim_named_param<P>{p}; }
+template <class G, class P>
+void copy_graph(const G& src, G& dst, const shim_named_param<P>&) { dst = src; }
+template <class G>
+void copy_graph(const G& src, G& dst) { dst = src; }
+}  // namespace boost
+
 // <boost/graph/iteration_macros.hpp>
 #define BGL_FORALL_VERTICES(VNAME, GNAME, GraphType) \
   for (GraphType::vertex_descriptor VNAME : boost::make_iterator_range(boost::vertices(GNAME)))

@@ -4,7 +4,12 @@
 #define IFTWT_SHIM_PCL_POINT_TYPES_H
 #include <cmath>
 #include <cstdint>
+#include <memory>
 #define pcl_isfinite(x) std::isfinite(x)
+namespace Eigen {
+template <class T>
+using aligned_allocator = std::allocator<T>;  // PCL's point vectors use Eigen's; alignment is moot here
+}
 namespace pcl {
 struct alignas(16) PointXYZ {
   float x = 0.f, y = 0.f, z = 0.f, pad_ = 1.f;

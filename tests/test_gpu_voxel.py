@@ -103,3 +103,53 @@ def test_reference_shaped_pipeline_on_the_voxel_graph(ctx):
     cost, label = ctx.ift(None, None)
     rcost, rlabel = orc.ift(roff, radj, cen[:, 3], rseeds, orc.POLICY_C)
     assert np.array_equal(cost, rcost) and np.array_equal(label, rlabel)
+
+
+def _sha(a) -> str:
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _binary_cloud():
+    pts = synth.scene_primitives(20_000, seed=0x1F77)
+    pts[:, 3] = np.where(np.sin(3.0 * pts[:, 0]) * np.cos(2.0 * pts[:, 1]) > 0, 255.0, 0.0)
+    return pts
+
+
+REF_GRAPH_CLOUDS = {
+    "ref_test_ply": ref_cloud,
+    "ref_test_ply_overlap5": ref_cloud,
+    "primitives20k": lambda: synth.scene_primitives(20_000, seed=0x1F66),
+    "binary20k": _binary_cloud,
+}
+
+
+@pytest.mark.parametrize("name", sorted(REF_GRAPH_CLOUDS))
+def test_against_the_reference_own_graph_and_ift(ctx, name):
+    """GPU vs the REFERENCE's graph.hpp + ift.hpp (compiled unmodified against oracle/shim; outputs
+    committed as tests/golden/ref_graph.json by tools/make_ref_graph_golden.py): resolution, voxel
+    centres and snapped intensities, adjacency, morphology, regional minima and IFT costs are
+    bit-exact; IFT labels are an admissible tie-break of the reference's rule."""
+    g = json.load(open(os.path.join(GOLD, "ref_graph.json")))[name]
+    pts = REF_GRAPH_CLOUDS[name]()
+    ctx.set_cloud(pts)
+    res = ctx.cloud_resolution(g["overlap"])
+    assert res == g["resolution"]
+    assert ctx.voxel_graph(res) == g["n_voxels"]
+    cen = ctx.get_cloud()
+    assert _sha(cen) == g["centres_sha256"]
+    off, adj = ctx.graph_csr()
+    assert _sha(off) == g["off_sha256"] and _sha(adj) == g["adj_sha256"]
+    for op in (orc.MORPH_BIN_ERODE, orc.MORPH_DILATE, orc.MORPH_ERODE, orc.MORPH_GRADIENT):
+        assert _sha(ctx.morph(op)) == g["morph_sha256"][str(op)], op
+    rm = ctx.regmin_seeds()
+    assert len(rm) == g["regmin_count"] and _sha(np.asarray(rm, np.int32)) == g["regmin_sha256"]
+    seeds = np.array(g["ift"]["seed_vertices"], np.int32)
+    cost, label = ctx.ift(None, seeds)
+    assert _sha(cost) == g["ift"]["cost_sha256"]
+    assert int(np.count_nonzero(cost < 500)) == g["ift"]["reached"]
+    assert orc.ift_audit(off, adj, cen[:, 3], seeds, cost, label) == 0
+    grad = ctx.morph(orc.MORPH_GRADIENT)
+    ctx.set_intensity(grad)                                  # Graph::pc_to_g write-back
+    assert _sha(ctx.get_cloud()[:, 3]) == g["values_after_pc_to_g_sha256"]
+    assert _sha(ctx.morph(orc.MORPH_ERODE)) == g["erode_gradient_sha256"]
