@@ -9,8 +9,9 @@ seeds, IFT watershed) over one synthetic cloud per rank.
   e2e       the same through the C ABI with HOST buffers: pinned host cloud in,
             host cost/label out, every step, inside the timed region
   roofline  the dominant kernel (k-NN fast path) against the measured HBM peak
-  cpu_baseline  the CPU oracle (a port of the reference's CPU path; the reference
-            itself cannot be built here) on a bounded sample of the same cloud
+  cpu_baseline  the CPU oracle (a port of the reference's CPU path; the reference as a
+            whole cannot be built here) on a bounded sample of the same cloud, plus the
+            reference's own ift.hpp (oracle/_ref) on a 20 k-point sample
 
 `--impl reference` times that CPU path as the reference arm.
 """
@@ -103,6 +104,37 @@ def run_cpu_path(pts: np.ndarray, k: int) -> float:
     return time.perf_counter() - t0
 
 
+def reference_ift_sample(gen: str, n_full: int, k: int, n_sample: int = 20_000):
+    """The REFERENCE's own IFT_PCD (ift.hpp compiled unmodified against oracle/shim — oracle/_ref,
+    built where /root/reference exists and shipped prebuilt) on the k-NN graph of a small slab of the
+    workload.  Its heap has an O(|Q|) remove() per decrease-key and its region bookkeeping spawns one
+    OpenMP task per vertex per region contact, so its cost grows faster than linearly: the figure is
+    reported for the stated sample only and is not extrapolated."""
+    try:
+        from oracle import pyoracle as orc
+        from oracle import pyref
+        if not pyref.available():
+            return None
+        pts = cpu_sample(gen, n_full, n_sample)
+        idx, _ = orc.knn_self(pts, k)
+        off, adj = orc.knn_graph(idx)
+        nrm = orc.normals(pts, idx)
+        lab, _, kept, _ = orc.region_growing(nrm, idx, THETA, 1.0, RG_MIN, RG_MAX)
+        seeds, _ = orc.rg_seeds(pts, lab, kept)
+        if len(seeds) == 0:
+            seeds = np.arange(0, len(pts), max(1, len(pts) // 16), dtype=np.int32)
+        t0 = time.perf_counter()
+        cost, root, *_ = pyref.ift(pts, off, adj, pts[np.asarray(seeds, np.int64), :3])
+        t = time.perf_counter() - t0
+        fcost, _ = orc.ift(off, adj, pts[:, 3], np.asarray(seeds, np.int32), orc.POLICY_R)
+        return {"kind": "reference", "what": "IFT_PCD of ift.hpp (unmodified) on the symmetric k-NN graph of the sample",
+                "points": int(len(pts)), "seeds": int(len(seeds)), "seconds": t, "points_per_s": len(pts) / t,
+                "costs_equal_port": bool(np.array_equal(cost, fcost)),
+                "note": "superlinear in the sample size (O(|Q|) heap remove, task-per-vertex region bookkeeping)"}
+    except Exception as e:  # the checker must never take the bench down
+        return {"kind": "reference", "error": repr(e)[:200]}
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -176,10 +208,13 @@ def reference_arm(args, gen, n_full, k, desc):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
         "config": {"workload": desc, "k": k, "points": n_full, "sample_points": len(pts),
-                   "note": "reference CPU path restated by oracle/ (the reference needs PCL/Boost and cannot "
-                           "be built in this image); OpenMP k-NN + normals, sequential region growing and IFT "
-                           "as in the reference"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": orc.num_threads(), "kind": "port", "sample": sample},
+                   "note": "reference CPU path restated by oracle/ (the reference as a whole needs PCL/Boost/VTK "
+                           "and cannot be built in this image): OpenMP k-NN + normals, sequential region growing "
+                           "and IFT as in the reference.  Its own graph.hpp / ift.hpp do compile against "
+                           "oracle/shim and pin this port bit for bit (tests/test_ref_*.py); ift.hpp itself is "
+                           "timed on a small sample in cpu_baseline.reference_ift"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": orc.num_threads(), "kind": "port", "sample": sample,
+                         "reference_ift": reference_ift_sample(gen, n_full, k)},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -389,7 +424,8 @@ def main():
             sample = cpu_sample(gen, n, args.cpu_sample)
             t = run_cpu_path(sample, k)
             cpu = {"value": len(sample) / t, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
-                   "sample": f"x-slab of the cloud holding {len(sample)} points, full pipeline once ({t:.1f} s)"}
+                   "sample": f"x-slab of the cloud holding {len(sample)} points, full pipeline once ({t:.1f} s)",
+                   "reference_ift": reference_ift_sample(gen, n, k)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,

@@ -6,17 +6,21 @@
 // bench.py may load it.  The product (iftwt_rg_b200/csrc, libiftwt.so) never
 // links, includes or calls anything in this directory.
 //
-// PARITY STATUS: *unpinned*.  The reference (enemy537/IFTWT_RG) ships no
-// tests, no golden vectors, and cannot be compiled here (PCL 1.8, Boost.Graph,
-// FLANN, Eigen, VTK are not installed; no network).  This file is a
-// dependency-free C++17 restatement of
-//   (a) the reference's own loops, cited as  file:line  of /root/reference, and
-//   (b) the PCL 1.8.1 / FLANN 1.9.1 / Eigen 3.3 routines those loops call,
-//       restated from the published algorithms ("[PCL-recall]": not
-//       checkable offline; each such routine is one clearly-named function).
-// It is cross-checked in tests/ against scipy.spatial.cKDTree, numpy.linalg,
-// scipy.sparse.csgraph and brute-force Python, which is the strongest pin
-// available in this image.
+// PARITY STATUS: pinned by the reference's OWN code for the rows the reference wrote itself,
+// unpinned for the PCL routines it calls.  The reference (enemy537/IFTWT_RG) ships no tests
+// and no golden vectors, and as a whole it cannot be compiled here (PCL 1.8, Boost.Graph, FLANN,
+// Eigen, VTK are not installed; no network).  This file is a dependency-free C++17 restatement of
+//   (a) the reference's own loops, cited as  file:line  of /root/reference.  graph.hpp, ift.hpp
+//       and globals.hpp DO compile, unmodified, against the small API stand-ins of oracle/shim
+//       (oracle/ref_ift_driver.cpp, oracle/ref_graph_driver.cpp -> oracle/_ref/*.so); their
+//       outputs — cloud resolution, voxel graph, morphology, pc_to_g, regional minima, IFT costs,
+//       root labels and the `mst` map — are committed under tests/golden/ref_*.{npz,json} and this
+//       file reproduces every one of them bit for bit (tests/test_ref_ift.py, test_ref_graph.py);
+//   (b) the PCL 1.8.1 / FLANN 1.9.1 / Eigen 3.3 routines those loops call (k-NN search, octree
+//       voxelisation, normal estimation, region growing), restated from the published algorithms
+//       ("[PCL-recall]": not checkable offline; each is one clearly-named function).  These stay
+//       UNPINNED by the reference and are cross-checked in tests/ against scipy.spatial.cKDTree,
+//       numpy.linalg, scipy.sparse.csgraph and brute-force Python.
 //
 // Conventions
 //   * points are rows of 4 floats {x, y, z, intensity}
