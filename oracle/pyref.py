@@ -146,3 +146,43 @@ class RefGraph:
         m = int(libg().ref_graph_ift(self._h, _p(seeds_xyz), C.c_int64(seeds_xyz.shape[0]), _p(cost), _p(root),
                                      _p(a), _p(b), _p(w), C.c_int64(cap)))
         return cost, root, a[:m], b[:m], w[:m]
+
+
+class RefGraCo:
+    """`GraCo gc(cloud_t, overlap)` of graco.hpp:47-56.  pts: n x {x, y, z, bits of the packed colour}."""
+
+    def __init__(self, pts, overlap: float = 5.0):
+        pts = np.ascontiguousarray(pts, np.float32)
+        g = libg()
+        g.ref_graco_create.restype = C.c_void_p
+        g.ref_graco_resolution.restype = C.c_double
+        g.ref_graco_cloud.restype = C.c_int64
+        g.ref_graco_morph.restype = C.c_int64
+        self._h = C.c_void_p(g.ref_graco_create(_p(pts), C.c_int64(pts.shape[0]), C.c_double(overlap)))
+        self._res = float(g.ref_graco_resolution(self._h))
+        self.n = int(g.ref_graco_cloud(self._h, None, None))
+
+    def close(self):
+        if self._h:
+            libg().ref_graco_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def resolution(self) -> float:
+        return self._res
+
+    def cloud(self):
+        xyz = np.empty((self.n, 3), np.float32)
+        rgb = np.empty(self.n, np.uint32)
+        libg().ref_graco_cloud(self._h, _p(xyz), _p(rgb))
+        return xyz, rgb
+
+    def morph(self, op: int):
+        rgb = np.empty(self.n, np.uint32)
+        assert libg().ref_graco_morph(self._h, C.c_int(op), _p(rgb)) == self.n
+        return rgb

@@ -7,8 +7,9 @@
 //
 // What is the reference's here: computeCloudResolution, initialize, optimizeGraph, find_p,
 // getCloud / g_to_pc, getAdjacencyList, copy_g, pc_to_g, morph_base and its five wrappers,
-// morph_gradient, morph_erode_gradient, getRegmin (graph.hpp:15-31, 34-66, 130-226, 228-371) and
-// all of IFT_PCD.  What is the shim's: k-NN search, the occupied-voxel set and its adjacency
+// morph_gradient, morph_erode_gradient, getRegmin (graph.hpp:15-31, 34-66, 130-226, 228-371), all of
+// IFT_PCD, and GraCo's constructor, optimizeGraph, getCloud and colour erode / dilate
+// (graco.hpp:19-64, 137-144, 176-179, 246-296, 301-351).  What is the shim's: k-NN search, the occupied-voxel set and its adjacency
 // (PCL's part of the work, restated from the published algorithm — SURVEY App. A.1 / A.2) and
 // the Boost.Graph containers.
 #include <fcntl.h>
@@ -16,13 +17,16 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <string>
 
 #include "globals.hpp"  // /root/reference
 #include <pcl/octree/octree_pointcloud_adjacency.h>
 #include <pcl/search/kdtree.h>
+#include <array>
 #include "graph.hpp"    // /root/reference
 #include "ift.hpp"      // /root/reference
+#include "graco.hpp"    // /root/reference
 
 namespace {
 struct Quiet {  // the reference prints counts and timings on stdout: park fd 1 on /dev/null
@@ -156,4 +160,53 @@ REF_API int64_t ref_graph_ift(void* hv, const float* seeds_xyz, int64_t ns, uint
     ++m;
   }
   return m;
+}
+
+// ---- GraCo (graco.hpp): `GraCo gc(cloud_t, 5.0); gc.morph_erode(cloud_g)` is what the live main()
+// runs (main.cpp:87-89).  pts4: n x {x, y, z, bits of 0xAARRGGBB} ----
+namespace {
+inline uint32_t pack_rgb(const global::PointT& p) { return ((uint32_t)p.r << 16) | ((uint32_t)p.g << 8) | p.b; }  // 0x00RRGGBB
+}
+REF_API void* ref_graco_create(const float* pts4, int64_t n, double overlap) {
+  global::CloudT::Ptr cloud(new global::CloudT());
+  for (int64_t i = 0; i < n; ++i) {
+    global::PointT p;
+    p.x = pts4[4 * i];
+    p.y = pts4[4 * i + 1];
+    p.z = pts4[4 * i + 2];
+    uint32_t w;
+    memcpy(&w, pts4 + 4 * i + 3, 4);
+    p.r = (w >> 16) & 0xFF;
+    p.g = (w >> 8) & 0xFF;
+    p.b = w & 0xFF;
+    cloud->push_back(p);
+  }
+  Quiet q;
+  return new GraCo(cloud, overlap);
+}
+REF_API void ref_graco_destroy(void* h) { delete (GraCo*)h; }
+REF_API double ref_graco_resolution(void*) {
+  return pcl::octree::OctreePointCloudAdjacency<global::PointT>::last_resolution();
+}
+static int64_t graco_out(const global::CloudT::Ptr& c, float* xyz, uint32_t* rgb) {
+  for (size_t i = 0; i < c->size() && rgb; ++i) {
+    if (xyz) {
+      xyz[3 * i] = c->points[i].x;
+      xyz[3 * i + 1] = c->points[i].y;
+      xyz[3 * i + 2] = c->points[i].z;
+    }
+    rgb[i] = pack_rgb(c->points[i]);
+  }
+  return (int64_t)c->size();
+}
+// getCloud() — graco.hpp:176-179
+REF_API int64_t ref_graco_cloud(void* h, float* xyz, uint32_t* rgb) { return graco_out(((GraCo*)h)->getCloud(), xyz, rgb); }
+// op: 3 dilate, 4 erode (enum MORPH_COLOR, graco.hpp:18)
+REF_API int64_t ref_graco_morph(void* h, int op, uint32_t* rgb) {
+  global::CloudT::Ptr c(new global::CloudT());
+  Quiet q;
+  if (op == 3) c = ((GraCo*)h)->morph_dilate(c);
+  else if (op == 4) c = ((GraCo*)h)->morph_erode(c);
+  else return -1;
+  return graco_out(c, nullptr, rgb);
 }

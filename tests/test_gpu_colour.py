@@ -78,3 +78,30 @@ def test_grey_and_otsu_prep_then_ift(ctx, otsu):
     cost, label = ctx.ift(None, seeds)
     rcost, rlabel = orc.ift(roff, radj, gray, seeds, orc.POLICY_C)
     assert np.array_equal(cost, rcost) and np.array_equal(label, rlabel)
+
+
+@pytest.mark.parametrize("name", ["graco_ref_test_ply_overlap5", "graco_primitives20k"])
+def test_against_the_reference_own_graco(ctx, name):
+    """GPU vs the REFERENCE's GraCo (graco.hpp compiled unmodified against oracle/shim; outputs in
+    tests/golden/ref_graph.json, tools/make_ref_graph_golden.py): resolution, voxel centres, snapped
+    colours and colour erode / dilate, bit-exact."""
+    import hashlib
+    import json
+
+    def sha(a):
+        return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+    g = json.load(open(os.path.join(GOLD, "ref_graph.json")))[name]
+    if name == "graco_ref_test_ply_overlap5":
+        pts = coloured(_ref_ply(), 3)
+    else:
+        pts = coloured(synth.scene_primitives(20_000, seed=0x1F88), 4)
+    ctx.set_cloud(pts)
+    res = ctx.cloud_resolution(g["overlap"])
+    assert res == g["resolution"]
+    assert ctx.voxel_graph(res) == g["n_voxels"]
+    got = ctx.get_cloud()
+    assert sha(got[:, :3]) == g["centres_xyz_sha256"]
+    assert sha(got[:, 3].copy().view(np.uint32) & 0xFFFFFF) == g["rgb_sha256"]
+    for op in (orc.MORPH_DILATE, orc.MORPH_ERODE):
+        assert sha(ctx.morph_rgb(op) & 0xFFFFFF) == g["morph_rgb_sha256"][str(op)], op

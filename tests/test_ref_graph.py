@@ -19,7 +19,8 @@ from oracle import pyref
 
 GOLD_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GOLD = json.load(open(os.path.join(GOLD_DIR, "ref_graph.json")))
-NAMES = [k for k in GOLD if not k.startswith("_")]
+NAMES = [k for k in GOLD if not k.startswith("_") and not k.startswith("graco_")]
+GRACO = [k for k in GOLD if k.startswith("graco_")]
 
 
 def sha(a) -> str:
@@ -92,6 +93,47 @@ def test_reference_reproduces_survey_numbers_on_test_ply():
     assert g["resolution"] == old["resolution"]
 
 
+def coloured(pts, seed):
+    rng = np.random.default_rng(seed)
+    n = len(pts)
+    base = np.clip(pts[:, 3].astype(np.int64), 0, 255)
+    r = np.clip(base + rng.integers(-20, 20, n), 0, 255)
+    g = np.clip(255 - base + rng.integers(-20, 20, n), 0, 255)
+    b = rng.integers(0, 4, n) * 64
+    word = (0xFF << 24) | (r << 16) | (g << 8) | b
+    out = pts.copy()
+    out[:, 3] = word.astype(np.uint32).view(np.float32)
+    return out
+
+
+def ref_cloud_colour():
+    xyz = np.load(os.path.join(GOLD_DIR, "ref_test_ply_xyz.npy"))
+    pts = np.zeros((len(xyz), 4), np.float32)
+    pts[:, :3] = xyz
+    pts[:, 3] = np.floor(127.5 + 127.5 * np.sin(40.0 * xyz[:, 0]))
+    return coloured(pts, 3)
+
+
+GRACO_CLOUDS = {
+    "graco_ref_test_ply_overlap5": ref_cloud_colour,
+    "graco_primitives20k": lambda: coloured(synth.scene_primitives(20_000, seed=0x1F88), 4),
+}
+
+
+@pytest.mark.parametrize("name", GRACO)
+def test_oracle_colour_graph_and_morphology_equal_reference_graco(name):
+    """GraCo gc(cloud_t, overlap); gc.morph_erode / morph_dilate — graco.hpp, what the live main() runs"""
+    g = GOLD[name]
+    pts = GRACO_CLOUDS[name]()
+    assert orc.cloud_resolution(pts, g["overlap"], 0) == g["resolution"]
+    cen, keys, off, adj, box = orc.voxel_graph(pts, g["resolution"])
+    assert len(cen) == g["n_voxels"] and sha(cen[:, :3]) == g["centres_xyz_sha256"]
+    rgb = cen[:, 3].copy().view(np.uint32)
+    assert sha(rgb & 0xFFFFFF) == g["rgb_sha256"]              # optimizeGraph: colour of the nearest point
+    for op in (orc.MORPH_DILATE, orc.MORPH_ERODE):
+        assert sha(orc.morph_rgb(off, adj, rgb, op) & 0xFFFFFF) == g["morph_rgb_sha256"][str(op)], op
+
+
 needs_ref = pytest.mark.skipif(
     not (pyref.graph_available() or os.path.exists(os.path.join(pyref.REFERENCE, "graph.hpp"))),
     reason="oracle/_ref/libref_graph.so is built where /root/reference exists")
@@ -112,3 +154,16 @@ def test_reference_live_equals_fixture(name):
         assert sha(r.regmin().astype(np.int32)) == g["regmin_sha256"]
         cost, root, a, b, w = r.ift(r.cloud()[np.array(g["ift"]["seed_vertices"]), :3])
         assert sha(cost) == g["ift"]["cost_sha256"] and sha(root) == g["ift"]["root_sha256"]
+
+
+@needs_ref
+def test_reference_graco_live_equals_fixture():
+    pyref.build()
+    name = "graco_primitives20k"
+    g = GOLD[name]
+    with pyref.RefGraCo(GRACO_CLOUDS[name](), g["overlap"]) as r:
+        assert r.resolution() == g["resolution"] and r.n == g["n_voxels"]
+        xyz, rgb = r.cloud()
+        assert sha(xyz) == g["centres_xyz_sha256"] and sha(rgb & 0xFFFFFF) == g["rgb_sha256"]
+        for op in (3, 4):
+            assert sha(r.morph(op) & 0xFFFFFF) == g["morph_rgb_sha256"][str(op)]

@@ -51,6 +51,34 @@ CASES = {
 N_SEEDS = 24
 
 
+def coloured(pts, seed):
+    """pcl::PointXYZRGB-style cloud: the 4th float carries the packed 0xFFRRGGBB word (tests/test_gpu_colour.py)"""
+    rng = np.random.default_rng(seed)
+    n = len(pts)
+    base = np.clip(pts[:, 3].astype(np.int64), 0, 255)
+    r = np.clip(base + rng.integers(-20, 20, n), 0, 255)
+    g = np.clip(255 - base + rng.integers(-20, 20, n), 0, 255)
+    b = rng.integers(0, 4, n) * 64
+    word = (0xFF << 24) | (r << 16) | (g << 8) | b
+    out = pts.copy()
+    out[:, 3] = word.astype(np.uint32).view(np.float32)
+    return out
+
+
+def ref_cloud_colour():
+    xyz = np.load(os.path.join(GOLD, "ref_test_ply_xyz.npy"))
+    pts = np.zeros((len(xyz), 4), np.float32)
+    pts[:, :3] = xyz
+    pts[:, 3] = np.floor(127.5 + 127.5 * np.sin(40.0 * xyz[:, 0]))
+    return coloured(pts, 3)
+
+
+GRACO_CASES = {
+    "graco_ref_test_ply_overlap5": (ref_cloud_colour, 5.0),          # main.cpp:87: GraCo gc(cloud_t, 5.0)
+    "graco_primitives20k": (lambda: coloured(synth.scene_primitives(20_000, seed=0x1F88), 4), 1.5),
+}
+
+
 def seed_vertices(V):
     return (np.arange(N_SEEDS, dtype=np.int64) * 7919 + 13) % V
 
@@ -58,7 +86,8 @@ def seed_vertices(V):
 def main():
     assert pyref.build() and pyref.graph_available(), "needs /root/reference (development container)"
     out = {"_comment": "outputs of the reference's own graph.hpp / ift.hpp (tools/make_ref_graph_golden.py); "
-                       "vertex order = ascending voxel Morton key; op ids = enum MORPH of graph.hpp:13, 5 = gradient"}
+                       "vertex order = ascending voxel Morton key; op ids = enum MORPH of graph.hpp:13, 5 = gradient; "
+                       "graco_* = GraCo of graco.hpp, colours as 0x00RRGGBB"}
     for name, (gen, overlap) in CASES.items():
         pts = gen()
         t0 = time.time()
@@ -85,6 +114,15 @@ def main():
         out[name] = e
         print(f"{name}: V={e['n_voxels']} arcs={e['n_arcs']} res={e['resolution']:.9g} regmin={e['regmin_count']} "
               f"reached={e['ift']['reached']} ({time.time() - t0:.1f} s)")
+    for name, (gen, overlap) in GRACO_CASES.items():
+        pts = gen()
+        with pyref.RefGraCo(pts, overlap) as g:
+            xyz, rgb = g.cloud()
+            e = {"n_points": int(len(pts)), "overlap": overlap, "resolution": g.resolution(), "n_voxels": g.n,
+                 "centres_xyz_sha256": sha(xyz), "rgb_sha256": sha(rgb & 0xFFFFFF),
+                 "morph_rgb_sha256": {str(op): sha(g.morph(op) & 0xFFFFFF) for op in (3, 4)}}
+        out[name] = e
+        print(f"{name}: V={e['n_voxels']} res={e['resolution']:.9g}")
     json.dump(out, open(os.path.join(GOLD, "ref_graph.json"), "w"), indent=1)
 
 
