@@ -218,11 +218,31 @@ def reference_arm(args, gen, n_full, k, desc):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout carries exactly ONE line, the JSON: everything libraries print there (NCCL's version
+    banner, the reference's own progress prints) goes to stderr instead."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
     args = parse()
+    quiet_stdout()
     gen, n_default, k_default, desc = WORKLOADS[args.workload]
     n = args.points or n_default
     k = args.k or k_default
@@ -437,7 +457,7 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu, "detail": extra,
         }
-        print(json.dumps(line))
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
