@@ -34,6 +34,10 @@
 #define KNN_RR_SMALL(E) ((E) == 1 ? 3 : (E) == 2 ? 5 : 10)
 #define KNN_RR_MAX(E) (KNN_CAP_OF(E) / 32)
 #define KEY_MAX 0xFFFFFFFFFFFFFFFFull
+#define GEN_CS 64  // general path: candidates below the cap that are ranked in one go
+// the 27 cells of a block ordered by distance from the centre; index = (dx+1) + 3 (dy+1) + 9 (dz+1)
+__constant__ unsigned char GEN_ORDER27[27] = {13, 4, 10, 12, 14, 16, 22, 1, 3, 5, 7, 9, 11, 15, 17, 19, 21, 23, 25, 0, 2, 6, 8, 18, 20, 24, 26};
+__device__ __forceinline__ int gen_order(int i) { return GEN_ORDER27[i]; }
 #define SID_NONE 0xFFFFFFFFu
 
 __device__ __forceinline__ u64 make_key(float d2, u32 orig) {
@@ -365,6 +369,12 @@ knn_general_kernel(GridView g, const float4* __restrict__ spts, const float4* __
   const u32 nw = (gridDim.x * blockDim.x) >> 5;
   const u32 total = EXTERNAL ? m_external : *count_ptr;
   WarpTopK<RL> top;
+  __shared__ u64 s_ckey[EXTERNAL ? 1 : 8][2 * GEN_CS];  // per warp: collected keys | keys by rank
+  __shared__ u32 s_csid[EXTERNAL ? 1 : 8][2 * GEN_CS];
+  u64* c_key = s_ckey[EXTERNAL ? 0 : (threadIdx.x >> 5)];
+  u64* o_key = c_key + GEN_CS;
+  u32* c_sid = s_csid[EXTERNAL ? 0 : (threadIdx.x >> 5)];
+  u32* o_sid = c_sid + GEN_CS;
   for (u32 it = gw; it < total; it += nw) {
     u32 row;
     int j0 = 0;
@@ -405,24 +415,77 @@ knn_general_kernel(GridView g, const float4* __restrict__ spts, const float4* __
           pend = g.cell_start[b];
         }
       }
-      for (int c27 = 0; c27 < 27; ++c27) {
-        u32 s = __shfl_sync(FULL, pstart, c27), e = __shfl_sync(FULL, pend, c27);
-        for (u32 base = s; base < e; base += 32) {
-          u32 pi = base + lane;
-          u64 ck = KEY_MAX;
-          if (pi < e) {
-            float4 P = spts[pi];
-            ck = make_key(dist2_exact(Q.x, Q.y, Q.z, P.x, P.y, P.z), __float_as_uint(P.w));
-          }
-          u64 thr = top.at_key(k - 1);
-          unsigned mask = __ballot_sync(FULL, ck < thr && ck <= cap);
-          while (mask) {
-            int src = __ffs(mask) - 1;
-            mask &= mask - 1;
-            u64 x = __shfl_sync(FULL, ck, src);
-            top.insert(x, base + (u32)src, lane);
+      // A query the fast path handed over with its k-th key as a cap needs exactly the candidates
+      // below the cap: the k it already found plus the few of the second ring that beat them.
+      // Inserting them one at a time into the sorted list was 60 % of this kernel's instructions
+      // (~80 per insertion, ncu source page); they are COLLECTED instead (ballot compaction into
+      // shared memory) and ranked against each other once — the rank is the list position.  More
+      // than GEN_CS of them (exact ties on the cap) and the pass is repeated with insertions.
+      bool collect = !EXTERNAL && j0 == 1 && j == 1;
+      for (int pass = 0; pass < 2; ++pass) {
+        u32 ccnt = 0;
+        for (int o27 = 0; o27 < 27; ++o27) {
+          // nearest cells first (centre, faces, edges, corners): the list fills with near points and
+          // its k-th key — the admission threshold — is tight before the far cells are read
+          const int c27 = gen_order(o27);
+          u32 s = __shfl_sync(FULL, pstart, c27), e = __shfl_sync(FULL, pend, c27);
+          for (u32 base = s; base < e; base += 32) {
+            u32 pi = base + lane;
+            u64 ck = KEY_MAX;
+            if (pi < e) {
+              float4 P = spts[pi];
+              ck = make_key(dist2_exact(Q.x, Q.y, Q.z, P.x, P.y, P.z), __float_as_uint(P.w));
+            }
+            if (collect) {
+              const bool p = ck <= cap;  // KEY_MAX (no point) never is: cap carries a finite distance
+              const unsigned m = __ballot_sync(FULL, p);
+              const u32 pos = ccnt + (u32)__popc(m & ((1u << lane) - 1u));
+              if (p && pos < GEN_CS) {
+                c_key[pos] = ck;
+                c_sid[pos] = pi;
+              }
+              ccnt += (u32)__popc(m);
+              continue;
+            }
+            u64 thr = top.at_key(k - 1);
+            unsigned mask = __ballot_sync(FULL, ck < thr && ck <= cap);
+            while (mask) {
+              int src = __ffs(mask) - 1;
+              mask &= mask - 1;
+              u64 x = __shfl_sync(FULL, ck, src);
+              top.insert(x, base + (u32)src, lane);
+            }
           }
         }
+        if (!collect) break;
+        collect = false;
+        if (ccnt > GEN_CS) continue;  // does not fit: second pass, by insertion
+        __syncwarp();
+        // rank = position in the sorted list (keys are unique: (d2, original index))
+        u64 mk[2];
+        int rk[2] = {0, 0};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) mk[e] = (u32)(lane + 32 * e) < ccnt ? c_key[lane + 32 * e] : KEY_MAX;
+        for (u32 i = 0; i < ccnt; ++i) {
+          const u64 x = c_key[i];
+          rk[0] += x < mk[0] ? 1 : 0;
+          rk[1] += x < mk[1] ? 1 : 0;
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          if ((u32)(lane + 32 * e) < ccnt) {
+            o_key[rk[e]] = mk[e];
+            o_sid[rk[e]] = c_sid[lane + 32 * e];
+          }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < RL; ++r) {
+          const u32 p = (u32)(r * 32 + lane);
+          top.key[r] = p < ccnt ? o_key[p] : KEY_MAX;
+          top.sid[r] = p < ccnt ? o_sid[p] : SID_NONE;
+        }
+        __syncwarp();
+        break;
       }
       // distance from the query to the nearest unscanned cell: faces of the block
       // that still have cells behind them
