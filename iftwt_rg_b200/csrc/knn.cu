@@ -140,6 +140,71 @@ __device__ __forceinline__ void cell_queries(const CellWarp& w, const float* __r
       // ranking loop below runs on whole pairs of uint4 words only
       if (lane < 7 && cnt + lane < CS) w.s_d2[cnt + lane] = 0xFFFFFFFFu;
       __syncwarp();
+      u32 kb = 0;  // bits of the k-th distance (set by the lane that owns it)
+      bool ranked = false;
+      if (E == 2 && tau < INFINITY) {
+        // ---- E == 2: a bitonic network over 64 packed keys, two per lane.  key = (q << 6) | position
+        // in the survivor list, q = (unsigned)(d2 * 6e7 / tau) < 2^26: the map d2 -> q is monotone, so
+        // keys with different q are in the order of their d2; two survivors with the same q (exact
+        // ties, or d2 closer than tau / 6e7: ~1e-5 of the queries) cannot be told apart here and the
+        // query goes through the comparison ranking below.  21 compare-exchange steps of ~5
+        // instructions against cnt^2 / 16 comparisons (ncu: 227 of the 560 instructions per query). ----
+        const float scale = __fdividef(6.0e7f, tau);
+        u32 ka = 0xFFFFFFFFu, kc = 0xFFFFFFFFu;  // list positions lane and lane + 32
+        if (lane < cnt) ka = ((u32)(__uint_as_float(w.s_d2[lane]) * scale) << 6) | (u32)lane;
+        if (lane + 32 < cnt) kc = ((u32)(__uint_as_float(w.s_d2[lane + 32]) * scale) << 6) | (u32)(lane + 32);
+        // every compare-exchange is ascending (the lower position keeps the smaller key): a merge of
+        // two sorted runs of k2 / 2 starts with the MIRROR step (partner = position ^ (k2 - 1)), then
+        // halves the distance.  Which side a lane is on depends on one bit of its number only.
+        const bool l1 = (lane & 1) == 0, l2 = (lane & 2) == 0, l4 = (lane & 4) == 0, l8 = (lane & 8) == 0,
+                   l16 = (lane & 16) == 0;
+#define CX(mask, lower)                                        \
+  {                                                            \
+    const u32 ta = __shfl_xor_sync(FULL, ka, mask), tc = __shfl_xor_sync(FULL, kc, mask); \
+    ka = (lower) ? min(ka, ta) : max(ka, ta);                  \
+    kc = (lower) ? min(kc, tc) : max(kc, tc);                  \
+  }
+        CX(1, l1);                                            // runs of 2
+        CX(3, l2);  CX(1, l1);                                // 4
+        CX(7, l4);  CX(2, l2);  CX(1, l1);                    // 8
+        CX(15, l8); CX(4, l4);  CX(2, l2); CX(1, l1);         // 16
+        CX(31, l16); CX(8, l8); CX(4, l4); CX(2, l2); CX(1, l1);  // 32: ka and kc are sorted runs
+        {  // 64: position p of the first run against position 63 - p = second run, lane 31 - p
+          const u32 tc = __shfl_xor_sync(FULL, kc, 31), ta = __shfl_xor_sync(FULL, ka, 31);
+          ka = min(ka, tc);
+          kc = max(kc, ta);
+        }
+        CX(16, l16); CX(8, l8); CX(4, l4); CX(2, l2); CX(1, l1);
+#undef CX
+        // sorted position lane holds ka, position lane + 32 holds kc; the successor of position 31 is 32
+        u32 na = __shfl_down_sync(FULL, ka, 1);
+        const u32 nc = __shfl_down_sync(FULL, kc, 1);
+        const u32 c0 = __shfl_sync(FULL, kc, 0);
+        if (lane == 31) na = c0;
+        const bool tie = ((ka >> 6) == (na >> 6) && na != 0xFFFFFFFFu) ||
+                         (lane < 31 && (kc >> 6) == (nc >> 6) && nc != 0xFFFFFFFFu);
+        if (!__any_sync(FULL, tie)) {
+          ranked = true;
+          u32* nrow = nbr + (size_t)qid * k;
+          float* drow = nd2 + (size_t)qid * k;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const u32 key = e ? kc : ka;
+            const int p = lane + 32 * e;
+            if (p < k) {  // cnt >= k: the first k positions hold survivors
+              const u32 i = key & 63u;
+              const u32 slot = w.s_slot[i], db = w.s_d2[i];
+              nrow[p] = w.s_id[slot];
+              drow[p] = __uint_as_float(db);
+              if (p == k - 1) {
+                kth[qid] = ((u64)db << 32) | (u64)__float_as_uint(w.s_pts[slot].w);
+                kb = db;
+              }
+            }
+          }
+        }
+      }
+      if (!ranked) {
       // ---- rank = output slot.  Ranks are counted on d2 alone (non-negative floats order
       // as unsigned ints); an exact d2 tie makes two ranks collide, which shows as a rank
       // sum below cnt(cnt-1)/2 and sends the query through the full (d2, index) compare. ----
@@ -187,7 +252,6 @@ __device__ __forceinline__ void cell_queries(const CellWarp& w, const float* __r
           for (int e = 0; e < E; ++e) rk[e] += (x < md[e] || (x == md[e] && xo < mo[e])) ? 1 : 0;
         }
       }
-      u32 kb = 0;  // bits of the k-th distance (set by the lane that owns it)
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         if (lane + 32 * e < cnt && rk[e] < k) {
@@ -200,6 +264,7 @@ __device__ __forceinline__ void cell_queries(const CellWarp& w, const float* __r
           }
         }
       }
+      }  // !ranked
       const float kd2 = __uint_as_float(__reduce_max_sync(FULL, kb));
       done = kd2 <= qb2[qid];
       tau = fmaxf(kd2 * grow, tiny);
