@@ -148,7 +148,8 @@ __device__ __forceinline__ void cell_queries(const CellWarp& w, const float* __r
         // keys with different q are in the order of their d2; two survivors with the same q (exact
         // ties, or d2 closer than tau / 6e7: ~1e-5 of the queries) cannot be told apart here and the
         // query goes through the comparison ranking below.  21 compare-exchange steps of ~5
-        // instructions against cnt^2 / 16 comparisons (ncu: 227 of the 560 instructions per query). ----
+        // instructions against cnt^2 / 16 comparisons (ncu: 227 of the 560 instructions per query).
+        // (E == 1, one key per lane, 15 steps: slower than ranking ~21 survivors — k = 16: 4.51 -> 4.99 ms.) ----
         const float scale = __fdividef(6.0e7f, tau);
         u32 ka = 0xFFFFFFFFu, kc = 0xFFFFFFFFu;  // list positions lane and lane + 32
         if (lane < cnt) ka = ((u32)(__uint_as_float(w.s_d2[lane]) * scale) << 6) | (u32)lane;
