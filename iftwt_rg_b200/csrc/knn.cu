@@ -624,7 +624,11 @@ int knn_run(iftwt_ctx* c, int k) {
     size_t sm = cell_kernel_smem(E);
     CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     const char* menv = getenv("IFTWT_KNN_MARGIN");
-    const float margin = menv ? (float)atof(menv) : 1.1f;  // swept on B200 (cfg3): 1.05 -> 5.76 ms, 1.12 -> 5.77, 1.25 -> 5.87, 1.4 -> 6.01
+    // survivors aimed at = margin * k + 2.  Comparison ranking (cost ~ cnt^2) wants few: swept on B200
+    // (cfg3): 1.05 -> 5.76 ms, 1.12 -> 5.77, 1.25 -> 5.87, 1.4 -> 6.01.  The 64-key network of E == 2 costs
+    // the same for any cnt <= 64, so a wider margin only saves threshold iterations: 1.1 -> 5.13 ms,
+    // 1.2 -> 5.10, 1.3 / 1.4 -> 5.09
+    const float margin = menv ? (float)atof(menv) : (E == 2 ? 1.3f : 1.1f);
     LAUNCH(c, kern, blocks, KNN_WARPS * 32, sm, g, spts, (const float*)c->qb2.as<float>(), k, tau0, margin,
            c->nbr.as<u32>(), c->nd2.as<float>(), c->kth.as<u64>(), c->fb_list.as<u32>(), fb_count);
   }
