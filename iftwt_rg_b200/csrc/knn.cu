@@ -26,7 +26,9 @@
 
 #include "common.cuh"
 
-#define KNN_WARPS 8
+// warps (= cells) per block.  A block holds its shared memory until its slowest warp is done; k <= 16:
+// 4 warps 4.26 ms against 4.51 with 8; k = 32: 5.18 against 5.09
+#define KNN_WARPS_OF(E) ((E) == 1 ? 4 : 8)
 #define KNN_CAP_OF(E) ((E) <= 2 ? 256 : 512)  // staged candidates per warp
 // Two compile-time round counts per E: the common case and the full buffer.  (Eight variants
 // made 9,144 SASS instructions and the kernel stalled on instruction fetch: ncu no_instruction
@@ -279,12 +281,13 @@ __device__ __forceinline__ void cell_queries(const CellWarp& w, const float* __r
 }
 
 template <int E>  // E = CS / 32 survivor slots per lane
-__global__ void __launch_bounds__(KNN_WARPS * 32)
+__global__ void __launch_bounds__(KNN_WARPS_OF(E) * 32)
 knn_cell_kernel(GridView g, const float4* __restrict__ spts, const float* __restrict__ qb2, int k,
                 float tau0, float margin, u32* __restrict__ nbr, float* __restrict__ nd2, u64* __restrict__ kth,
                 u32* __restrict__ fb_list, u32* __restrict__ fb_count) {
   constexpr int CS = 32 * E;
   constexpr int KNN_CAP = KNN_CAP_OF(E);
+  constexpr int KNN_WARPS = KNN_WARPS_OF(E);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* s_pts_all = (float4*)smem_raw;                        // [W][CAP] staged candidates
   u32* s_d2_all = (u32*)(s_pts_all + KNN_WARPS * KNN_CAP);      // [W][CS] survivor d2 bits (16 B aligned)
@@ -594,7 +597,7 @@ knn_general_kernel(GridView g, const float4* __restrict__ spts, const float4* __
 // ---------------------------------------------------------------------------
 static size_t cell_kernel_smem(int E) {
   int CS = 32 * E, cap = KNN_CAP_OF(E);
-  return (size_t)KNN_WARPS * (cap * 16 + cap * 4 + CS * 4 + CS * 4) + 16;
+  return (size_t)KNN_WARPS_OF(E) * (cap * 16 + cap * 4 + CS * 4 + CS * 4) + 16;
 }
 
 int knn_run(iftwt_ctx* c, int k) {
@@ -616,7 +619,6 @@ int knn_run(iftwt_ctx* c, int k) {
   const GridView& g = c->grid;
   float tau0 = (float)(g.cell * g.cell * 0.6);
   const float4* spts = c->spts.as<float4>();
-  unsigned blocks = div_up(g.n_cells, KNN_WARPS);
   cudaEventRecord(c->ev0[IFTWT_STAGE_KNN_CELL], c->stream);
   {
     const int E = k <= 16 ? 1 : (k <= 32 ? 2 : 4);
@@ -629,7 +631,8 @@ int knn_run(iftwt_ctx* c, int k) {
     // the same for any cnt <= 64, so a wider margin only saves threshold iterations: 1.1 -> 5.13 ms,
     // 1.2 -> 5.10, 1.3 / 1.4 -> 5.09
     const float margin = menv ? (float)atof(menv) : (E == 2 ? 1.3f : 1.1f);
-    LAUNCH(c, kern, blocks, KNN_WARPS * 32, sm, g, spts, (const float*)c->qb2.as<float>(), k, tau0, margin,
+    const unsigned blocks = div_up(g.n_cells, KNN_WARPS_OF(E));
+    LAUNCH(c, kern, blocks, KNN_WARPS_OF(E) * 32, sm, g, spts, (const float*)c->qb2.as<float>(), k, tau0, margin,
            c->nbr.as<u32>(), c->nd2.as<float>(), c->kth.as<u64>(), c->fb_list.as<u32>(), fb_count);
   }
   cudaEventRecord(c->ev1[IFTWT_STAGE_KNN_CELL], c->stream);
