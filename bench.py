@@ -406,7 +406,7 @@ def main():
             pass
         roofline = {"bound": "hbm", "kernel": "knn_cell_kernel", "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
-                    "active_limiter": "instruction issue (ncu: 86 % issue-active, ALU pipe 62 %, DRAM 6 %), not HBM",
+                    "active_limiter": "instruction issue (ncu: 79 % issue-active, ALU pipe 63 %, LSU pipe 56 %, DRAM 7 %), not HBM",
                     "peak_source": which, "algorithmic_bytes_per_launch": alg_bytes,
                     "avg_launch_ms": knn_ms}
         nrm_ms = stage_ms.get("normals", 0.0)
