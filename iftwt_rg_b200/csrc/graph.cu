@@ -65,34 +65,37 @@ knn_mutual_kernel(const u32* __restrict__ nbr, const float* __restrict__ nd2, co
   }
 }
 
-// scatter the one-way arcs u -> v into v's reverse list.  One warp per FILL_V consecutive
-// vertices, lane j <-> arc j: the chain row entry -> atomicAdd (with return) -> store is pure
-// latency, so each lane keeps FILL_V independent chains in flight (one warp per vertex:
-// 1.69 ms at 10 M points, k = 32, 36 long-scoreboard stall cycles per issue).
-#define FILL_V 4
+// scatter the one-way arcs u -> v into v's reverse list.  One THREAD per vertex walks the set bits
+// of its one-way mask (1.5 on average, 5 % of the arcs), two arcs at a time: the chain row entry ->
+// atomicAdd (with return) -> store is pure latency, and only whole threads' worth of it is worth
+// keeping in flight.  (One warp per vertex, lane <-> arc: 1.69 ms at 10 M points, k = 32; one warp per
+// four vertices, four chains per lane: 0.88 ms — 95 % of the lanes had no arc.)
 __global__ void __launch_bounds__(256)
 graph_fill_rev_kernel(const u32* __restrict__ nbr, const u64* __restrict__ ow_mask, u32 n, int k,
                       const u32* __restrict__ roff, u32* __restrict__ cursor, u32* __restrict__ radj) {
-  const u32 u0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * FILL_V;
-  const int lane = threadIdx.x & 31;
-  if (u0 >= n) return;
-  u64 mask[FILL_V];
-#pragma unroll
-  for (int i = 0; i < FILL_V; ++i) mask[i] = u0 + i < n ? ow_mask[u0 + i] : 0ull;
-  for (int base = 0; base < k; base += 32) {
-    const int j = base + lane;
-    u32 v[FILL_V], pos[FILL_V], off[FILL_V];
-#pragma unroll
-    for (int i = 0; i < FILL_V; ++i)
-      v[i] = (j < k && ((mask[i] >> j) & 1ull)) ? nbr[(size_t)(u0 + i) * k + j] : SID_NONE;
-#pragma unroll
-    for (int i = 0; i < FILL_V; ++i) {
-      off[i] = v[i] != SID_NONE ? roff[v[i]] : 0u;
-      pos[i] = v[i] != SID_NONE ? atomicAdd(&cursor[v[i]], 1u) : 0u;
+  const u32 u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n) return;
+  u64 mask = ow_mask[u];
+  const u32* row = nbr + (size_t)u * k;
+  while (mask) {
+    const int j0 = __ffsll((long long)mask) - 1;
+    mask &= mask - 1;
+    int j1 = -1;
+    if (mask) {
+      j1 = __ffsll((long long)mask) - 1;
+      mask &= mask - 1;
     }
-#pragma unroll
-    for (int i = 0; i < FILL_V; ++i)
-      if (v[i] != SID_NONE) radj[off[i] + pos[i]] = u0 + i;
+    const u32 v0 = row[j0];
+    const u32 v1 = j1 >= 0 ? row[j1] : SID_NONE;
+    const u32 o0 = roff[v0];
+    const u32 p0 = atomicAdd(&cursor[v0], 1u);
+    u32 o1 = 0, p1 = 0;
+    if (v1 != SID_NONE) {
+      o1 = roff[v1];
+      p1 = atomicAdd(&cursor[v1], 1u);
+    }
+    radj[o0 + p0] = u;
+    if (v1 != SID_NONE) radj[o1 + p1] = u;
   }
 }
 
@@ -143,7 +146,7 @@ int graph_build(iftwt_ctx* c) {
   ENSURE(c, c->g_adj, (n_rev + 1) * 4);
   CU_TRY(c, cudaMemsetAsync(rdeg, 0, (size_t)n * 4, c->stream));  // now the fill cursor
   if (n_rev) {
-    LAUNCH(c, graph_fill_rev_kernel, div_up((size_t)div_up(n, FILL_V) * 32, 256), 256, 0, c->nbr.as<u32>(), c->ow_mask.as<u64>(),
+    LAUNCH(c, graph_fill_rev_kernel, div_up(n, 256), 256, 0, c->nbr.as<u32>(), c->ow_mask.as<u64>(),
            n, k, roff, rdeg, c->g_adj.as<u32>());
     CHECK_LAUNCH(c);
   }
