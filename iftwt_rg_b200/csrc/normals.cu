@@ -44,13 +44,13 @@ __device__ __forceinline__ double spec_atan2_ypos(double y, double x) {
 __device__ __forceinline__ double spec_cos(double x) {
   double x2 = x * x, c = 1.0;
 #pragma unroll
-  for (int n = 13; n >= 1; --n) c = 1.0 - (x2 / (double)((2 * n - 1) * (2 * n))) * c;
+  for (int n = 13; n >= 1; --n) c = 1.0 - (x2 * (1.0 / (double)((2 * n - 1) * (2 * n)))) * c;
   return c;
 }
 __device__ __forceinline__ double spec_sin(double x) {
   double x2 = x * x, s = 1.0;
 #pragma unroll
-  for (int n = 13; n >= 1; --n) s = 1.0 - (x2 / (double)((2 * n) * (2 * n + 1))) * s;
+  for (int n = 13; n >= 1; --n) s = 1.0 - (x2 * (1.0 / (double)((2 * n) * (2 * n + 1)))) * s;
   return x * s;
 }
 

@@ -263,12 +263,12 @@ double spec_atan2_ypos(double y, double x) {  // y >= 0
 }
 double spec_cos(double x) {  // |x| <= ~1.1
   double x2 = x * x, c = 1.0;
-  for (int n = 13; n >= 1; --n) c = 1.0 - (x2 / (double)((2 * n - 1) * (2 * n))) * c;
+  for (int n = 13; n >= 1; --n) c = 1.0 - (x2 * (1.0 / (double)((2 * n - 1) * (2 * n)))) * c;
   return c;
 }
 double spec_sin(double x) {
   double x2 = x * x, s = 1.0;
-  for (int n = 13; n >= 1; --n) s = 1.0 - (x2 / (double)((2 * n) * (2 * n + 1))) * s;
+  for (int n = 13; n >= 1; --n) s = 1.0 - (x2 * (1.0 / (double)((2 * n) * (2 * n + 1)))) * s;
   return x * s;
 }
 
