@@ -74,3 +74,51 @@ def test_graco_adapter_runs_the_live_main(tmp_path):
     """main.cpp:80-89 (GraCo gc(cloud_t, 5.0); gc.morph_erode) and the Otsu prep through the adapters."""
     out = subprocess.run([_build_cpp(tmp_path, "graco_test")], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "graco ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_adapter_vs_ref_compiles(tmp_path):
+    assert os.path.exists(_build_cpp(tmp_path, "adapter_vs_ref"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["ref_test_ply_overlap5", "primitives20k"])
+def test_adapters_reproduce_the_reference_own_classes(tmp_path, name):
+    """`Graph gg(cloud, overlap); gg.morph_*(); gg.getRegmin(); IFT_PCD ift(gg, seeds); gg.pc_to_g(...)`
+    written against include/iftwt_adapters.hpp give what the same calls give on the REFERENCE's own
+    graph.hpp / ift.hpp (compiled unmodified; tests/golden/ref_graph.json), bit for bit."""
+    import hashlib
+    import json
+
+    import numpy as np
+    from iftwt_rg_b200 import synth
+
+    def sha(path):
+        return hashlib.sha256(open(path, "rb").read()).hexdigest()
+
+    gold_dir = os.path.join(ROOT, "tests", "golden")
+    g = json.load(open(os.path.join(gold_dir, "ref_graph.json")))[name]
+    if name == "primitives20k":
+        pts = synth.scene_primitives(20_000, seed=0x1F66)
+    else:
+        xyz = np.load(os.path.join(gold_dir, "ref_test_ply_xyz.npy"))
+        pts = np.zeros((len(xyz), 4), np.float32)
+        pts[:, :3] = xyz
+        pts[:, 3] = np.floor(127.5 + 127.5 * np.sin(40.0 * xyz[:, 0]) * np.cos(31.0 * xyz[:, 1]))
+    np.ascontiguousarray(pts, np.float32).tofile(tmp_path / "cloud.f32")
+    np.array(g["ift"]["seed_vertices"], np.int64).tofile(tmp_path / "seeds.i64")
+    out = tmp_path / "out"
+    out.mkdir()
+    exe = _build_cpp(tmp_path, "adapter_vs_ref")
+    r = subprocess.run([exe, str(tmp_path / "cloud.f32"), repr(g["overlap"]), str(tmp_path / "seeds.i64"), str(out)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "adapter ok" in r.stdout, r.stdout + r.stderr
+    assert np.fromfile(out / "resolution.f64", np.float64)[0] == g["resolution"]
+    assert sha(out / "centres.f32") == g["centres_sha256"]
+    assert sha(out / "off.u32") == g["off_sha256"] and sha(out / "adj.u32") == g["adj_sha256"]
+    for op in (1, 3, 4, 5):
+        assert sha(out / f"morph{op}.f32") == g["morph_sha256"][str(op)], op
+    assert hashlib.sha256(np.fromfile(out / "regmin.u32", np.uint32).astype(np.int32).tobytes()).hexdigest() == \
+        g["regmin_sha256"]
+    assert sha(out / "cost.u32") == g["ift"]["cost_sha256"]
+    assert sha(out / "after_pc_to_g.f32") == g["values_after_pc_to_g_sha256"]
+    assert sha(out / "erode_gradient.f32") == g["erode_gradient_sha256"]
