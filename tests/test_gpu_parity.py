@@ -48,9 +48,19 @@ def test_knn_ties_duplicates_and_small_clouds(ctx):
     pts = np.zeros((20000, 4), np.float32)
     pts[:, :3] = g
     ctx.set_cloud(pts)
-    for k in (8, 16, 40):
+    for k in (8, 16, 24, 32, 40):   # 24 / 32: the sorting-network path must hand exact ties to the comparison ranking
         idx, d2 = ctx.knn(k)
         ridx, rd2 = orc.knn_self(pts, k)
+        assert np.array_equal(idx, ridx), k
+        assert np.array_equal(d2, rd2), k
+    # near ties: the lattice with a jitter of a few ulp — distances that differ only in their last bits
+    # share a quantised key in the sorting network and have to be ordered by their exact d2
+    jit = pts.copy()
+    jit[:, :3] += (rng.integers(-2, 3, size=(20000, 3)) * 2.0 ** -22).astype(np.float32)
+    ctx.set_cloud(jit)
+    for k in (20, 32):
+        idx, d2 = ctx.knn(k)
+        ridx, rd2 = orc.knn_self(jit, k)
         assert np.array_equal(idx, ridx), k
         assert np.array_equal(d2, rd2), k
     # fewer points than k
