@@ -142,8 +142,10 @@ __global__ void occupancy_kernel(const u64* __restrict__ keys, u32 n, u32 stride
   if (threadIdx.x >= 1 && threadIdx.x < 17 && sh[threadIdx.x]) atomicAdd(&sums[threadIdx.x], sh[threadIdx.x]);
 }
 
+// KeyT = u32 when the Morton code of a cell fits 32 bits (a third less sort traffic), else u64
+template <class KeyT>
 __global__ void cell_key_kernel(const float4* __restrict__ pts, u32 n, double ox, double oy, double oz,
-                                double inv_cell, int dx, int dy, int dz, u64* __restrict__ keys,
+                                double inv_cell, int dx, int dy, int dz, KeyT* __restrict__ keys,
                                 u32* __restrict__ vals) {
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -151,8 +153,12 @@ __global__ void cell_key_kernel(const float4* __restrict__ pts, u32 n, double ox
   int ix = min(dx - 1, max(0, (int)floor(((double)p.x - ox) * inv_cell)));
   int iy = min(dy - 1, max(0, (int)floor(((double)p.y - oy) * inv_cell)));
   int iz = min(dz - 1, max(0, (int)floor(((double)p.z - oz) * inv_cell)));
-  keys[i] = morton3((u32)ix, (u32)iy, (u32)iz);
+  keys[i] = (KeyT)morton3((u32)ix, (u32)iy, (u32)iz);
   vals[i] = i;
+}
+__global__ void widen_keys_kernel(const u32* __restrict__ k32, u32 m, u64* __restrict__ k64) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) k64[i] = (u64)k32[i];
 }
 
 // sorted gather: float4 {x,y,z,bits(orig)} + inverse permutation + per-point
@@ -312,16 +318,27 @@ int grid_build(iftwt_ctx* c, int k) {
   u64* k1 = c->keys_alt.as<u64>();
   u32* v0 = c->vals_alt.as<u32>();
   u32* perm = c->perm.as<u32>();
-  LAUNCH(c, cell_key_kernel, div_up(n, 256), 256, 0, pts, n, lo[0], lo[1], lo[2], 1.0 / cell, dim[0],
-         dim[1], dim[2], k0, v0);
-  CHECK_LAUNCH(c);
-  {
+  const bool narrow = 3 * bits <= 32;  // cfg3: 30 bits
+  u32* k0n = (u32*)k0;
+  u32* k1n = (u32*)k1;
+  if (narrow) {
+    LAUNCH(c, cell_key_kernel<u32>, div_up(n, 256), 256, 0, pts, n, lo[0], lo[1], lo[2], 1.0 / cell, dim[0],
+           dim[1], dim[2], k0n, v0);
+    CHECK_LAUNCH(c);
+    size_t tb = 0;
+    CU_TRY(c, cub::DeviceRadixSort::SortPairs(nullptr, tb, k0n, k1n, v0, perm, (int)n, 0, 3 * bits, c->stream));
+    ENSURE(c, c->tmp, tb);
+    CU_TRY(c, cub::DeviceRadixSort::SortPairs(c->tmp.p, tb, k0n, k1n, v0, perm, (int)n, 0, 3 * bits, c->stream));
+  } else {
+    LAUNCH(c, cell_key_kernel<u64>, div_up(n, 256), 256, 0, pts, n, lo[0], lo[1], lo[2], 1.0 / cell, dim[0],
+           dim[1], dim[2], k0, v0);
+    CHECK_LAUNCH(c);
     size_t tb = 0;
     CU_TRY(c, cub::DeviceRadixSort::SortPairs(nullptr, tb, k0, k1, v0, perm, (int)n, 0, 3 * bits, c->stream));
     ENSURE(c, c->tmp, tb);
     CU_TRY(c, cub::DeviceRadixSort::SortPairs(c->tmp.p, tb, k0, k1, v0, perm, (int)n, 0, 3 * bits, c->stream));
-    c->stats.kernel_launches += 2 + (3 * bits + 7) / 8;
   }
+  c->stats.kernel_launches += 2 + (3 * bits + 7) / 8;
   ENSURE(c, c->qb2, (size_t)n * 4);
   LAUNCH(c, gather_sorted_kernel, div_up(n, 256), 256, 0, pts, perm, n, lo[0], lo[1], lo[2], 1.0 / cell,
          cell, dim[0], dim[1], dim[2], c->spts.as<float4>(), c->inv.as<u32>(), c->qb2.as<float>());
@@ -332,7 +349,15 @@ int grid_build(iftwt_ctx* c, int k) {
   ENSURE(c, c->cell_cnt, (size_t)n * 4);
   ENSURE(c, c->cell_start, ((size_t)n + 1) * 4);
   u32* d_nruns = (u32*)(sc + 40);
-  {
+  if (narrow) {  // unique 32-bit keys land in the (now free) unsorted key buffer and are widened below
+    size_t tb = 0;
+    CU_TRY(c, cub::DeviceRunLengthEncode::Encode(nullptr, tb, k1n, k0n, c->cell_cnt.as<u32>(), d_nruns, (int)n,
+                                                 c->stream));
+    ENSURE(c, c->tmp, tb);
+    CU_TRY(c, cub::DeviceRunLengthEncode::Encode(c->tmp.p, tb, k1n, k0n, c->cell_cnt.as<u32>(), d_nruns, (int)n,
+                                                 c->stream));
+    c->stats.kernel_launches += 2;
+  } else {
     size_t tb = 0;
     CU_TRY(c, cub::DeviceRunLengthEncode::Encode(nullptr, tb, k1, c->cell_key.as<u64>(),
                                                  c->cell_cnt.as<u32>(), d_nruns, (int)n, c->stream));
@@ -345,6 +370,10 @@ int grid_build(iftwt_ctx* c, int k) {
   CU_TRY(c, cudaStreamSynchronize(c->stream));
   u32 n_cells = (u32)hs[40];
   if (n_cells == 0 || n_cells > n) return ctx_fail(c, IFTWT_ERR_CUDA, "cell table build failed");
+  if (narrow) {
+    LAUNCH(c, widen_keys_kernel, div_up(n_cells, 256), 256, 0, (const u32*)k0n, n_cells, c->cell_key.as<u64>());
+    CHECK_LAUNCH(c);
+  }
   LAUNCH(c, set_u32_kernel, 1, 1, 0, c->cell_start.as<u32>(), 0u);
   {
     size_t tb = 0;
