@@ -280,14 +280,22 @@ __device__ __forceinline__ void cell_queries(const CellWarp& w, const float* __r
   }
 }
 
-template <int E>  // E = CS / 32 survivor slots per lane
+// CAP = staged candidates per warp.  The first pass (SECOND = false) runs one warp per occupied cell
+// with CAP = KNN_CAP_OF(E); a cell whose 3x3x3 block holds more (1 % of the cells of cfg3, 97 k of
+// its 104 k fallback queries — all of them below 384 candidates) is appended to `ovf_list` and
+// answered by a SECOND launch of the same code with a larger staging buffer (fewer warps resident,
+// but few cells) instead of by the general path, which costs ~8 times as much per query.
+template <int E, int CAP, bool SECOND>  // E = CS / 32 survivor slots per lane
 __global__ void __launch_bounds__(KNN_WARPS_OF(E) * 32)
 knn_cell_kernel(GridView g, const float4* __restrict__ spts, const float* __restrict__ qb2, int k,
                 float tau0, float margin, u32* __restrict__ nbr, float* __restrict__ nd2, u64* __restrict__ kth,
-                u32* __restrict__ fb_list, u32* __restrict__ fb_count) {
+                u32* __restrict__ fb_list, u32* __restrict__ fb_count, u32* __restrict__ ovf_list,
+                u32* __restrict__ ovf_count, int cap_second) {
   constexpr int CS = 32 * E;
-  constexpr int KNN_CAP = KNN_CAP_OF(E);
+  constexpr int KNN_CAP = CAP;
   constexpr int KNN_WARPS = KNN_WARPS_OF(E);
+  constexpr int RR_SMALL = SECOND ? CAP / 32 : KNN_RR_SMALL(E);
+  constexpr int RR_MAX = CAP / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* s_pts_all = (float4*)smem_raw;                        // [W][CAP] staged candidates
   u32* s_d2_all = (u32*)(s_pts_all + KNN_WARPS * KNN_CAP);      // [W][CS] survivor d2 bits (16 B aligned)
@@ -295,11 +303,14 @@ knn_cell_kernel(GridView g, const float4* __restrict__ spts, const float* __rest
   u32* s_slot_all = s_id_all + KNN_WARPS * KNN_CAP;             // [W][CS] survivor slots
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const u32 ci = blockIdx.x * KNN_WARPS + warp;
-  if (ci >= g.n_cells) return;  // warps are independent: no block-level barrier below
   float4* s_pts = s_pts_all + warp * KNN_CAP;
   u32* s_id = s_id_all + warp * KNN_CAP;
   const unsigned FULL = 0xffffffffu;
+  // warps are independent: no block-level barrier below
+  const u32 n_items = SECOND ? *ovf_count : g.n_cells;
+  const u32 stride = gridDim.x * KNN_WARPS;
+  for (u32 item = blockIdx.x * KNN_WARPS + warp; item < n_items; item += stride) {
+  const u32 ci = SECOND ? ovf_list[item] : item;
 
   // ---- the 27 cells of the block ----
   u32 cx, cy, cz;
@@ -326,11 +337,16 @@ knn_cell_kernel(GridView g, const float4* __restrict__ spts, const float* __rest
   const u32 qs = __shfl_sync(FULL, nstart, 13), qn = __shfl_sync(FULL, ncnt, 13);
   const u32 qoff = __shfl_sync(FULL, excl, 13);
 
+  if (!SECOND && M > KNN_CAP && M <= cap_second) {  // crowded: the second launch stages it
+    if (lane == 0) ovf_list[atomicAdd(ovf_count, 1u)] = ci;
+    return;
+  }
   if (M > KNN_CAP || M < k) {  // too crowded to stage, or not enough candidates: general path
     u32 base = 0;
     if (lane == 0) base = atomicAdd(fb_count, qn);
     base = __shfl_sync(FULL, base, 0);
     for (u32 t = lane; t < qn; t += 32) fb_list[base + t] = qs + t;
+    if (SECOND) continue;
     return;
   }
 
@@ -348,7 +364,7 @@ knn_cell_kernel(GridView g, const float4* __restrict__ spts, const float* __rest
   // the compiled round count covers the staged rounds; the unstaged slots it touches hold +inf
   // coordinates, so their distance is +inf and no threshold ever admits them
   const int R = (M + 31) >> 5;
-  const int RRu = R <= KNN_RR_SMALL(E) ? KNN_RR_SMALL(E) : KNN_RR_MAX(E);
+  const int RRu = R <= RR_SMALL ? RR_SMALL : RR_MAX;
   for (int t = M + lane; t < RRu * 32; t += 32) s_pts[t] = make_float4(INFINITY, INFINITY, INFINITY, 0.f);
   __syncwarp();
 
@@ -361,8 +377,11 @@ knn_cell_kernel(GridView g, const float4* __restrict__ spts, const float* __rest
   w.qs = qs;
   w.qn = qn;
   w.qoff = qoff;
-  if (R <= KNN_RR_SMALL(E)) cell_queries<E, KNN_RR_SMALL(E)>(w, qb2, k, tau0, margin, nbr, nd2, kth, fb_list, fb_count, lane);
-  else cell_queries<E, KNN_RR_MAX(E)>(w, qb2, k, tau0, margin, nbr, nd2, kth, fb_list, fb_count, lane);
+  if (R <= RR_SMALL) cell_queries<E, RR_SMALL>(w, qb2, k, tau0, margin, nbr, nd2, kth, fb_list, fb_count, lane);
+  else cell_queries<E, RR_MAX>(w, qb2, k, tau0, margin, nbr, nd2, kth, fb_list, fb_count, lane);
+  if (!SECOND) break;
+  __syncwarp();  // the next cell of this warp restages the buffers
+  }
 }
 
 template <int RL>
@@ -595,10 +614,11 @@ knn_general_kernel(GridView g, const float4* __restrict__ spts, const float4* __
 }
 
 // ---------------------------------------------------------------------------
-static size_t cell_kernel_smem(int E) {
-  int CS = 32 * E, cap = KNN_CAP_OF(E);
+static size_t cell_kernel_smem(int E, int cap) {
+  int CS = 32 * E;
   return (size_t)KNN_WARPS_OF(E) * (cap * 16 + cap * 4 + CS * 4 + CS * 4) + 16;
 }
+#define KNN_CAP2 384  // second launch (k <= 32): every crowded cell of cfg3 holds fewer candidates than this
 
 int knn_run(iftwt_ctx* c, int k) {
   if (k < 1 || k > 64) return ctx_fail(c, IFTWT_ERR_INVALID, "k must be in [1, 64], got %d", k);
@@ -613,17 +633,20 @@ int knn_run(iftwt_ctx* c, int k) {
   ENSURE(c, c->nbr, n * k * 4);
   ENSURE(c, c->nd2, n * k * 4);
   ENSURE(c, c->kth, n * 8);
-  ENSURE(c, c->fb_list, n * 4);
+  ENSURE(c, c->fb_list, n * 8);  // [n] fallback queries | [n] crowded cells for the second launch
   u32* fb_count = (u32*)(c->scalars.as<int>() + 48);
-  CU_TRY(c, cudaMemsetAsync(fb_count, 0, 4, c->stream));
+  u32* ovf_count = fb_count + 1;
+  u32* ovf_list = c->fb_list.as<u32>() + n;
+  CU_TRY(c, cudaMemsetAsync(fb_count, 0, 8, c->stream));
   const GridView& g = c->grid;
   float tau0 = (float)(g.cell * g.cell * 0.6);
   const float4* spts = c->spts.as<float4>();
   cudaEventRecord(c->ev0[IFTWT_STAGE_KNN_CELL], c->stream);
   {
     const int E = k <= 16 ? 1 : (k <= 32 ? 2 : 4);
-    auto kern = E == 1 ? knn_cell_kernel<1> : (E == 2 ? knn_cell_kernel<2> : knn_cell_kernel<4>);
-    size_t sm = cell_kernel_smem(E);
+    auto kern = E == 1 ? knn_cell_kernel<1, KNN_CAP_OF(1), false>
+              : (E == 2 ? knn_cell_kernel<2, KNN_CAP_OF(2), false> : knn_cell_kernel<4, KNN_CAP_OF(4), false>);
+    size_t sm = cell_kernel_smem(E, KNN_CAP_OF(E));
     CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     const char* menv = getenv("IFTWT_KNN_MARGIN");
     // survivors aimed at = margin * k + 2.  Comparison ranking (cost ~ cnt^2) wants few: swept on B200
@@ -632,8 +655,18 @@ int knn_run(iftwt_ctx* c, int k) {
     // 1.2 -> 5.10, 1.3 / 1.4 -> 5.09
     const float margin = menv ? (float)atof(menv) : (E == 2 ? 1.3f : 1.1f);
     const unsigned blocks = div_up(g.n_cells, KNN_WARPS_OF(E));
+    const int cap2 = E <= 2 ? KNN_CAP2 : 0;
     LAUNCH(c, kern, blocks, KNN_WARPS_OF(E) * 32, sm, g, spts, (const float*)c->qb2.as<float>(), k, tau0, margin,
-           c->nbr.as<u32>(), c->nd2.as<float>(), c->kth.as<u64>(), c->fb_list.as<u32>(), fb_count);
+           c->nbr.as<u32>(), c->nd2.as<float>(), c->kth.as<u64>(), c->fb_list.as<u32>(), fb_count, ovf_list,
+           ovf_count, cap2);
+    if (cap2) {  // crowded cells: the same code with a larger staging buffer, warps stride over the list
+      auto kern2 = E == 1 ? knn_cell_kernel<1, KNN_CAP2, true> : knn_cell_kernel<2, KNN_CAP2, true>;
+      const size_t sm2 = cell_kernel_smem(E, KNN_CAP2);
+      CU_TRY(c, cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+      LAUNCH(c, kern2, (unsigned)c->sm_count * 3, KNN_WARPS_OF(E) * 32, sm2, g, spts, (const float*)c->qb2.as<float>(),
+             k, tau0, margin, c->nbr.as<u32>(), c->nd2.as<float>(), c->kth.as<u64>(), c->fb_list.as<u32>(), fb_count,
+             ovf_list, ovf_count, 0);
+    }
   }
   cudaEventRecord(c->ev1[IFTWT_STAGE_KNN_CELL], c->stream);
   c->ev_set[IFTWT_STAGE_KNN_CELL] = true;
