@@ -417,7 +417,7 @@ def main():
                 traffic = int(tr["dram_bytes_read"]) + int(tr["dram_bytes_write"])
         except Exception:
             pass
-        roofline = {"bound": "hbm", "kernel": "knn_cell_kernel", "achieved": achieved, "peak": peak,
+        roofline = {"bound": "hbm", "kernel": "knn_cell_kernel (first launch + the crowded-cell launch, one event pair)", "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
                     "active_limiter": "instruction issue (ncu: 79 % issue-active, ALU pipe 63 %, LSU pipe 56 %, DRAM 7 %), not HBM",
                     "peak_source": which, "algorithmic_bytes_per_launch": alg_bytes,
