@@ -29,7 +29,9 @@
 // warps (= cells) per block.  A block holds its shared memory until its slowest warp is done; k <= 16:
 // 4 warps 4.26 ms against 4.51 with 8; k = 32: 5.18 against 5.09
 #define KNN_WARPS_OF(E) ((E) == 1 ? 4 : 8)
-#define KNN_CAP_OF(E) ((E) <= 2 ? 256 : 512)  // staged candidates per warp
+// staged candidates per warp.  (E == 2 with 192 for one more resident block and the cells above it left to
+// the second launch: 5.45 ms against 5.22.)
+#define KNN_CAP_OF(E) ((E) <= 2 ? 256 : 512)
 // Two compile-time round counts per E: the common case and the full buffer.  (Eight variants
 // made 9,144 SASS instructions and the kernel stalled on instruction fetch: ncu no_instruction
 // 4.2 per issue, profiles/r01_knn_cell_kernel_v3_ncu_full.txt.)
