@@ -35,7 +35,9 @@
 // Two compile-time round counts per E: the common case and the full buffer.  (Eight variants
 // made 9,144 SASS instructions and the kernel stalled on instruction fetch: ncu no_instruction
 // 4.2 per issue, profiles/r01_knn_cell_kernel_v3_ncu_full.txt.  A third count of 6 for E == 2 — a third of
-// cfg3's cells need exactly six rounds — grew the kernel from 2,700 to 3,800 instructions: 5.22 -> 5.91 ms.)
+// cfg3's cells need exactly six rounds — grew the kernel from 2,700 to 3,800 instructions: 5.22 -> 5.91 ms;
+// with the ordering / row-write part factored out of the round-count template (one copy, 2,350 instructions
+// for two counts: 5.25 ms; 2,760 for three: 5.42 ms) it still lost.)
 #define KNN_RR_SMALL(E) ((E) == 1 ? 3 : (E) == 2 ? 5 : 10)
 #define KNN_RR_MAX(E) (KNN_CAP_OF(E) / 32)
 #define KEY_MAX 0xFFFFFFFFFFFFFFFFull
