@@ -110,3 +110,82 @@ def test_reference_live_random_graphs(seed):
     assert np.array_equal(a, oa) and np.array_equal(b, ob) and np.array_equal(w, ow)
     ccost, _ = orc.ift(off, adj, pts[:, 3], seeds, orc.POLICY_C)
     assert np.array_equal(cost, ccost)
+
+
+@needs_ref
+def test_reference_live_property_small_graphs():
+    """Property test (hypothesis): on arbitrary small graphs — isolated vertices, self-contained
+    components, weights of 0 and >= MAX_COST, seeds on heavy vertices, duplicate seeds — the oracle's
+    literal restatement reproduces the reference's own IFT_PCD, and every label policy its costs."""
+    from hypothesis import given, settings, strategies as st
+    pyref.build()
+
+    @st.composite
+    def cases(draw):
+        n = draw(st.integers(2, 40))
+        m = draw(st.integers(0, 4 * n))
+        edges = draw(st.lists(st.tuples(st.integers(0, n - 1), st.integers(0, n - 1)), min_size=m, max_size=m))
+        w = draw(st.lists(st.sampled_from([0, 1, 2, 3, 5, 8, 13, 250, 499, 500, 700]), min_size=n, max_size=n))
+        seeds = draw(st.lists(st.integers(0, n - 1), min_size=1, max_size=6))
+        return n, edges, w, seeds
+
+    @settings(max_examples=60, deadline=None)
+    @given(cases())
+    def run(case):
+        n, edges, w, seeds = case
+        nb = [set() for _ in range(n)]
+        for a, b in edges:
+            if a != b:
+                nb[a].add(b)
+                nb[b].add(a)
+        off = np.zeros(n + 1, np.uint32)
+        adj = []
+        for i in range(n):
+            adj += sorted(nb[i])
+            off[i + 1] = len(adj)
+        adj = np.array(adj if adj else [0], np.uint32)[:off[n]]
+        pts = np.zeros((n, 4), np.float32)
+        pts[:, 0] = np.arange(n)                       # distinct positions: search_p matches exactly one vertex
+        pts[:, 3] = w
+        sv = np.array(seeds, np.int32)                  # duplicates allowed: they collapse (ift.hpp:138)
+        cost, root, a, b, mw = pyref.ift(pts, off, adj, pts[sv, :3])
+        ocost, olabel, oa, ob, ow = orc.ift_literal_mst(off, adj, pts[:, 3], sv)
+        assert np.array_equal(cost, ocost) and np.array_equal(root, olabel)
+        assert np.array_equal(a, oa) and np.array_equal(b, ob) and np.array_equal(mw, ow)
+        for policy in (orc.POLICY_C, orc.POLICY_R):
+            pc, pl = orc.ift(off, adj, pts[:, 3], sv, policy)
+            assert np.array_equal(pc, cost)
+            assert orc.ift_audit(off, adj, pts[:, 3], sv, pc, pl) == 0
+
+        run()
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", range(5))
+def test_reference_live_non_integer_weights(seed):
+    """The reference truncates float costs to unsigned (ift.hpp:203).  The product path
+    refuses non-integer weights; the oracle's literal restatement still follows the reference through them."""
+    pyref.build()
+    rng = np.random.default_rng(70 + seed)
+    for _ in range(40):
+        n = int(rng.integers(3, 40))
+        nb = [set() for _ in range(n)]
+        for _ in range(3 * n):
+            a, b = rng.integers(0, n, 2)
+            if a != b:
+                nb[a].add(int(b))
+                nb[b].add(int(a))
+        off = np.zeros(n + 1, np.uint32)
+        adj = []
+        for i in range(n):
+            adj += sorted(nb[i])
+            off[i + 1] = len(adj)
+        adj = np.array(adj if adj else [0], np.uint32)[:off[n]]
+        pts = np.zeros((n, 4), np.float32)
+        pts[:, 0] = np.arange(n)
+        pts[:, 3] = rng.choice([0.5, 1.0, 1.5, 2.25, 2.75, 3.0, 7.9, 8.1, 499.5, 500.0], n)
+        sv = rng.integers(0, n, 3).astype(np.int32)
+        cost, root, a, b, w = pyref.ift(pts, off, adj, pts[sv, :3])
+        ocost, olabel, oa, ob, ow = orc.ift_literal_mst(off, adj, pts[:, 3], sv)
+        assert np.array_equal(cost, ocost) and np.array_equal(root, olabel)
+        assert np.array_equal(a, oa) and np.array_equal(b, ob) and np.array_equal(w, ow)
