@@ -167,3 +167,15 @@ def test_reference_graco_live_equals_fixture():
         assert sha(xyz) == g["centres_xyz_sha256"] and sha(rgb & 0xFFFFFF) == g["rgb_sha256"]
         for op in (3, 4):
             assert sha(r.morph(op) & 0xFFFFFF) == g["morph_rgb_sha256"][str(op)]
+
+
+def test_shim_headers_unit(tmp_path):
+    """oracle/shim: the container, k-NN and octree stand-ins behave as the reference's results assume
+    (tests/cpp/shim_test.cpp)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "shim_test")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(root, "oracle", "shim"),
+                           os.path.join(root, "tests", "cpp", "shim_test.cpp"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "shim ok" in out.stdout, out.stdout + out.stderr
