@@ -4,7 +4,7 @@
 // Test infrastructure (like everything under oracle/): nothing under iftwt_rg_b200/ links or
 // calls it.  Built by `make -C oracle ref` into oracle/_ref/libref_ift.so against the
 // stand-in headers of oracle/shim (README there); used by tests/ to pin the oracle's literal
-// restatement (orc_ift_literal_mst) and by tools/make_ref_ift_golden.py to write the fixtures.
+// restatement (orc_ift_literal_mst) and by tests/golden/make_ref_ift_golden.py to write the fixtures.
 //
 // What is the reference's here: copy_graph, add_seeds, search_p, compute_watershed,
 // find_and_swap, r_info (ift.hpp:5-23, 97-250) and the priority queue with its O(|Q|) remove()

@@ -5,7 +5,7 @@ on the reference's test.ply (with the deterministic intensity texture the tests 
 synthetic scene.  Large arrays are stored as SHA-256 of their bytes.  Run in the development
 container, where /root/reference exists:
 
-    python tools/make_ref_graph_golden.py
+    python tests/golden/make_ref_graph_golden.py
 """
 import hashlib
 import json
@@ -15,7 +15,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from iftwt_rg_b200 import synth  # noqa: E402
 from oracle import pyref  # noqa: E402
@@ -85,7 +85,7 @@ def seed_vertices(V):
 
 def main():
     assert pyref.build() and pyref.graph_available(), "needs /root/reference (development container)"
-    out = {"_comment": "outputs of the reference's own graph.hpp / ift.hpp (tools/make_ref_graph_golden.py); "
+    out = {"_comment": "outputs of the reference's own graph.hpp / ift.hpp (tests/golden/make_ref_graph_golden.py); "
                        "vertex order = ascending voxel Morton key; op ids = enum MORPH of graph.hpp:13, 5 = gradient; "
                        "graco_* = GraCo of graco.hpp, colours as 0x00RRGGBB"}
     for name, (gen, overlap) in CASES.items():

@@ -4,14 +4,14 @@
 oracle/ref_ift_driver.cpp) on small graphs.  Run in the development container, where
 /root/reference exists; the fixtures travel to the GPU box, the reference does not.
 
-    python tools/make_ref_ift_golden.py
+    python tests/golden/make_ref_ift_golden.py
 """
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from iftwt_rg_b200 import synth  # noqa: E402
 from oracle import pyoracle as orc  # noqa: E402

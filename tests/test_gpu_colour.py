@@ -83,7 +83,7 @@ def test_grey_and_otsu_prep_then_ift(ctx, otsu):
 @pytest.mark.parametrize("name", ["graco_ref_test_ply_overlap5", "graco_primitives20k"])
 def test_against_the_reference_own_graco(ctx, name):
     """GPU vs the REFERENCE's GraCo (graco.hpp compiled unmodified against oracle/shim; outputs in
-    tests/golden/ref_graph.json, tools/make_ref_graph_golden.py): resolution, voxel centres, snapped
+    tests/golden/ref_graph.json, tests/golden/make_ref_graph_golden.py): resolution, voxel centres, snapped
     colours and colour erode / dilate, bit-exact."""
     import hashlib
     import json

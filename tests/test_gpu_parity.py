@@ -300,7 +300,7 @@ def test_segment_with_gradient_weights(ctx):
 @pytest.mark.parametrize("name", ["knn8_3k", "knn16_6k"])
 def test_ift_against_the_reference_own_code(ctx, name):
     """GPU vs the REFERENCE's IFT_PCD (ift.hpp compiled unmodified, outputs committed as
-    tests/golden/ref_ift_*.npz by tools/make_ref_ift_golden.py): the graph the GPU builds is the
+    tests/golden/ref_ift_*.npz by tests/golden/make_ref_ift_golden.py): the graph the GPU builds is the
     fixture's, costs are bit-exact, labels are an admissible tie-break; disagreements are counted."""
     import os
     z = np.load(os.path.join(os.path.dirname(__file__), "golden", f"ref_ift_{name}.npz"))

@@ -127,7 +127,7 @@ REF_GRAPH_CLOUDS = {
 @pytest.mark.parametrize("name", sorted(REF_GRAPH_CLOUDS))
 def test_against_the_reference_own_graph_and_ift(ctx, name):
     """GPU vs the REFERENCE's graph.hpp + ift.hpp (compiled unmodified against oracle/shim; outputs
-    committed as tests/golden/ref_graph.json by tools/make_ref_graph_golden.py): resolution, voxel
+    committed as tests/golden/ref_graph.json by tests/golden/make_ref_graph_golden.py): resolution, voxel
     centres and snapped intensities, adjacency, morphology, regional minima and IFT costs are
     bit-exact; IFT labels are an admissible tie-break of the reference's rule."""
     g = json.load(open(os.path.join(GOLD, "ref_graph.json")))[name]

@@ -3,7 +3,7 @@
 oracle/_ref/libref_graph.so is graph.hpp + ift.hpp + globals.hpp of /root/reference compiled
 UNMODIFIED (oracle/ref_graph_driver.cpp) against the API stand-ins of oracle/shim.  Its outputs on
 the reference's test.ply (two overlaps) and two synthetic scenes are committed as
-tests/golden/ref_graph.json (tools/make_ref_graph_golden.py; big arrays as SHA-256).  Pinned here:
+tests/golden/ref_graph.json (tests/golden/make_ref_graph_golden.py; big arrays as SHA-256).  Pinned here:
 computeCloudResolution, the voxel graph (centres, snapped intensities, adjacency), the four
 morphology operators + gradient, pc_to_g write-back, getRegmin, and IFT_PCD on that graph."""
 import hashlib

@@ -2,7 +2,7 @@
 
 oracle/_ref/libref_ift.so is ift.hpp + globals.hpp of /root/reference compiled UNMODIFIED
 (oracle/ref_ift_driver.cpp) against the API stand-ins of oracle/shim; its outputs on five
-graphs are committed as tests/golden/ref_ift_*.npz (tools/make_ref_ift_golden.py).  These tests
+graphs are committed as tests/golden/ref_ift_*.npz (tests/golden/make_ref_ift_golden.py).  These tests
 pin, on those fixtures and live when the library is present:
 
 * the oracle's literal restatement (orc_ift_literal_mst: cost, root label and the `mst` map of
