@@ -58,7 +58,7 @@ def parse():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--points", type=int, default=0)
     ap.add_argument("--k", type=int, default=0)
-    ap.add_argument("--cpu-sample", type=int, default=400_000)
+    ap.add_argument("--cpu-sample", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-inflight", type=int, default=2,
