@@ -52,8 +52,18 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert not bad.search(txt), f
-    for f in ("iftwt.h",):
-        assert not bad.search(open(os.path.join(ROOT, "include", f)).read())
+    for f in os.listdir(os.path.join(ROOT, "include")):
+        assert not bad.search(open(os.path.join(ROOT, "include", f)).read()), f
+    # neither do the example, the tools or the reference checker's third-party stand-ins (pyref included)
+    for d in ("examples", "tools"):
+        for f in os.listdir(os.path.join(ROOT, d)):
+            if f.endswith((".py", ".cpp", ".hpp", ".h")):
+                assert not bad.search(open(os.path.join(ROOT, d, f), errors="ignore").read()), f
+    bad_ref = re.compile(r"(from\s+oracle|import\s+oracle|pyref|libref_|oracle/_ref|oracle/shim)")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                assert not bad_ref.search(open(os.path.join(dp, f), errors="ignore").read()), f
 
 
 def test_no_gpu_means_loud_failure_not_fallback():
