@@ -58,7 +58,15 @@ def parse():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--points", type=int, default=0)
     ap.add_argument("--k", type=int, default=0)
-    ap.add_argument("--cpu-sample", type=int, default=1_000_000)
+    ap.add_argument("--cpu-sample", type=int, default=1_000_000,
+                    help="points of the x-slab the cpu_baseline leg of the GPU arm runs once")
+    ap.add_argument("--ref-sample", type=int, default=500_000,
+                    help="points of the x-slab every step of --impl reference runs")
+    ap.add_argument("--cpu-threads", type=int, default=0,
+                    help="OpenMP threads of the CPU arm (0 = every core this process may run on)")
+    ap.add_argument("--no-full-size-cpu", action="store_true",
+                    help="--impl reference: skip the single full-size pass (N = 1 only) that checks the slab figure")
+    ap.add_argument("--no-parity", action="store_true", help="skip detail.parity (GPU vs oracle on the cpu sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-inflight", type=int, default=2,
@@ -93,6 +101,15 @@ def cpu_sample(gen: str, n_full: int, n_sample: int) -> np.ndarray:
     xs = np.sort(pts[:, 0])
     hi = xs[min(len(xs) - 1, n_sample)]
     return np.ascontiguousarray(pts[pts[:, 0] < hi])
+
+
+def cpu_threads(args) -> int:
+    """torchrun exports OMP_NUM_THREADS=1: the CPU arm would silently run on one core at N > 1.  The
+    thread count is set explicitly, to every core the process may run on, and reported."""
+    from oracle import pyoracle as orc
+    t = args.cpu_threads or len(os.sched_getaffinity(0))
+    orc.set_threads(t)
+    return orc.num_threads()
 
 
 def run_cpu_path(pts: np.ndarray, k: int) -> float:
@@ -197,32 +214,89 @@ class ClockSampler:
 
 def reference_arm(args, gen, n_full, k, desc):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    from oracle import pyoracle as orc
-    pts = cpu_sample(gen, n_full, args.cpu_sample)
+    cores = cpu_threads(args)
+    pts = cpu_sample(gen, n_full, args.ref_sample)
     for _ in range(min(args.warmup, 1)):
         run_cpu_path(pts[: max(1000, len(pts) // 20)], k)
     times = [run_cpu_path(pts, k) for _ in range(max(1, args.steps))]
     t = float(np.mean(times))
     v = len(pts) / t
     sample = f"x-slab of the {n_full}-point cloud holding {len(pts)} points, full pipeline per step"
+    full = None
+    if world == 1 and not args.no_full_size_cpu and len(pts) < n_full:
+        # the slab figure is an extrapolation: check it once against the whole cloud
+        whole = make_cloud(gen, n_full)
+        tf = run_cpu_path(whole, k)
+        full = {"points": n_full, "seconds": tf, "points_per_s": n_full / tf, "cores": cores,
+                "slab_over_full": v / (n_full / tf)}
+        del whole
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,
+        "steps": max(1, args.steps), "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
-        "config": {"workload": desc, "k": k, "points": n_full, "sample_points": len(pts),
+        "config": {"workload": desc, "k": k, "points": n_full, "sample_points": len(pts), "same_config": False,
                    "note": "reference CPU path restated by oracle/ (the reference as a whole needs PCL/Boost/VTK "
                            "and cannot be built in this image): OpenMP k-NN + normals, sequential region growing "
-                           "and IFT as in the reference.  Its own graph.hpp / ift.hpp do compile against "
+                           "and IFT as in the reference, on an x-slab of the workload's cloud (same scene, same "
+                           "density).  Its own graph.hpp / ift.hpp do compile against "
                            "oracle/shim and pin this port bit for bit (tests/test_ref_*.py); ift.hpp itself is "
                            "timed on a small sample in cpu_baseline.reference_ift"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": orc.num_threads(), "kind": "port", "sample": sample,
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "full_size_once": full,
                          "reference_ift": reference_ift_sample(gen, n_full, k)},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def gpu_vs_oracle_parity(ctx, api, pts: np.ndarray, k: int) -> dict:
+    """GPU vs the oracle on the cpu sample (the slab the CPU baseline ran on), counted — the numbers the
+    north star asks for next to the throughput: costs and policy-C labels must be equal; labels under
+    the reference's abstract first-offer rule (policy R, ift.hpp:196-205) may differ at ties only, and
+    those are counted separately.  Plus the GPU against the REFERENCE's own IFT_PCD on the committed
+    fixture (tests/golden/ref_ift_knn16_6k.npz, ift.hpp compiled unmodified)."""
+    from oracle import pyoracle as orc
+    out = {"sample_points": int(len(pts)), "k": k}
+    rg = api.RgParams(RG_MIN, RG_MAX, k, THETA, 1.0)
+    ctx.set_cloud(pts)
+    cost, label, ns = ctx.segment(k, k, rg)
+    idx, _ = orc.knn_self(pts, k)
+    off, adj = orc.knn_graph(idx)
+    nrm = orc.normals(pts, idx)
+    lab, _, kept, _ = orc.region_growing(nrm, idx, THETA, 1.0, RG_MIN, RG_MAX)
+    seeds, _ = orc.rg_seeds(pts, lab, kept)
+    ccost, clabel = orc.ift(off, adj, pts[:, 3], seeds, orc.POLICY_C)
+    _, rlabel = orc.ift(off, adj, pts[:, 3], seeds, orc.POLICY_R)
+    out.update({
+        "seeds": int(ns), "seeds_oracle": int(kept),
+        "cost_mismatches_vs_oracle": int(np.count_nonzero(cost != ccost)),
+        "label_mismatches_vs_oracle_policy_C": int(np.count_nonzero(label != clabel)),
+        "tie_only_label_disagreements_vs_policy_R": int(np.count_nonzero(label != rlabel)),
+        "tie_audit_violations": int(orc.ift_audit(off, adj, pts[:, 3], seeds, cost, label)),
+    })
+    try:
+        z = np.load(os.path.join(ROOT, "tests", "golden", "ref_ift_knn16_6k.npz"))
+        fp, fk = z["pts"], int(z["k"])
+        ctx.set_cloud(fp)
+        foff, fadj = ctx.knn_graph(fk)
+        q = np.zeros((len(z["seeds_xyz"]), 4), np.float32)
+        q[:, :3] = z["seeds_xyz"]
+        sidx, _ = ctx.knn_query(q, 1)
+        fcost, flabel = ctx.ift(None, sidx[:, 0].astype(np.int32))
+        out["reference_fixture"] = {
+            "name": "ref_ift_knn16_6k (the reference's own IFT_PCD, ift.hpp unmodified)", "points": int(len(fp)),
+            "adjacency_equal": bool(np.array_equal(foff, z["off"]) and np.array_equal(fadj, z["adj"])),
+            "cost_mismatches": int(np.count_nonzero(fcost != z["ref_cost"])),
+            "tie_only_label_disagreements": int(np.count_nonzero(flabel != z["ref_root"])),
+            "tie_audit_violations": int(orc.ift_audit(foff, fadj, fp[:, 3], sidx[:, 0].astype(np.int32), fcost, flabel)),
+        }
+    except Exception as e:  # the checker must never take the bench down
+        out["reference_fixture"] = {"error": repr(e)[:200]}
+    return out
 
 
 _REAL_STDOUT = None
@@ -453,12 +527,17 @@ def main():
         }
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            from oracle import pyoracle as orc
+            cores = cpu_threads(args)
             sample = cpu_sample(gen, n, args.cpu_sample)
             t = run_cpu_path(sample, k)
-            cpu = {"value": len(sample) / t, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+            cpu = {"value": len(sample) / t, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"x-slab of the cloud holding {len(sample)} points, full pipeline once ({t:.1f} s)",
                    "reference_ift": reference_ift_sample(gen, n, k)}
+            if not args.no_parity:
+                try:
+                    extra["parity"] = gpu_vs_oracle_parity(ctx, api, sample, k)
+                except Exception as e:  # reported, never fatal: the timed numbers above stand on their own
+                    extra["parity"] = {"error": repr(e)[:300]}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,

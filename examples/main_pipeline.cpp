@@ -2,7 +2,7 @@
 // include/iftwt_adapters.hpp.  Build:
 //   g++ -std=c++14 -Iinclude examples/main_pipeline.cpp -Liftwt_rg_b200/lib -liftwt
 //       -Wl,-rpath,$PWD/iftwt_rg_b200/lib -o main_pipeline
-// Input: a .ply file (include/iftwt_io.hpp), a raw little-endian float32 file of {x,y,z,intensity} records, or a small built-in
+// Input: a .ply or .pcd file (include/iftwt_io.hpp), a raw little-endian float32 file of {x,y,z,intensity} records, or a small built-in
 // scene when no file is given (the reference's ../cloud/lucy_gray.ply is absent from its tree).
 #include <cstdio>
 #include <cstdlib>
@@ -13,8 +13,9 @@
 
 static global::CloudI::Ptr load_or_make(const char* path) {
   global::CloudI::Ptr cloud(new global::CloudI());
-  if (path && std::string(path).size() > 4 && std::string(path).substr(std::string(path).size() - 4) == ".ply") {
-    iftwt::io::loadPLYFile(path, *cloud);                                        // main.cpp:92
+  const std::string ext = path && std::string(path).size() > 4 ? std::string(path).substr(std::string(path).size() - 4) : "";
+  if (ext == ".ply" || ext == ".pcd") {
+    iftwt::io::load(path, *cloud);                                               // main.cpp:92 (loadPLYFile / loadPCDFile)
     return cloud;
   }
   if (path) {
@@ -29,17 +30,19 @@ static global::CloudI::Ptr load_or_make(const char* path) {
     std::fclose(f);
     return cloud;
   }
+  // a staircase of eight steps: sixteen planar patches of 800 - 2,000 voxels each, so that the reference's
+  // own region-growing parameters (main.cpp:112-119: 50 / 10000 / 50 / 3 degrees / 1.0) yield seeds
   unsigned s = 12345u;
   auto u = [&s]() { s = s * 1664525u + 1013904223u; return (float)(s >> 8) * (1.0f / 16777216.0f); };
   for (int i = 0; i < 60000; ++i) {
     global::PointI p;
-    if (i % 2) {  // plane, dark
-      p.x = 4.f * u() - 2.f; p.y = 4.f * u() - 2.f; p.z = 0.002f * (u() - 0.5f);
-      p.intensity = (float)(40 + (int)(8.f * u()));
-    } else {      // sphere, bright
-      float z = 2.f * u() - 1.f, a = 6.2831853f * u(), r = std::sqrt(1.f - z * z);
-      p.x = r * std::cos(a); p.y = r * std::sin(a); p.z = 1.2f + z;
-      p.intensity = (float)(200 + (int)(8.f * u()));
+    const int step = i % 8;
+    if ((i / 8) % 3 != 2) {  // tread, dark
+      p.x = 0.5f * ((float)step + u()); p.y = 2.f * u(); p.z = 0.25f * (float)step + 0.001f * (u() - 0.5f);
+      p.intensity = (float)(40 + 10 * step + (int)(4.f * u()));
+    } else {                 // riser, bright
+      p.x = 0.5f * (float)step + 0.001f * (u() - 0.5f); p.y = 2.f * u(); p.z = 0.25f * ((float)step - u());
+      p.intensity = (float)(200 - 10 * step + (int)(4.f * u()));
     }
     cloud->push_back(p);
   }
@@ -63,10 +66,10 @@ int main(int argc, char** argv) {
     normal_estimator.compute(normals);
 
     FlatPoint<global::PointI, iftwt::types::Normal> reg(gg);                     // main.cpp:111-119
-    reg.setMinClusterSize(20);
-    reg.setMaxClusterSize(100000);
+    reg.setMinClusterSize(50);
+    reg.setMaxClusterSize(10000);
     reg.setNumberOfNeighbours(50);
-    reg.setSmoothnessThreshold(20.0f / 180.0f * 3.14159265f);
+    reg.setSmoothnessThreshold(3.0f / 180.0f * 3.14159265f);
     reg.setCurvatureThreshold(1.0f);
     global::Cloud::Ptr centroid_cloud = reg.getCentroidsCloud();                 // main.cpp:121
 

@@ -216,7 +216,9 @@ int graph_export(iftwt_ctx* c, u32* h_off, u32* h_adj, size_t cap, size_t* n_arc
   const int k = c->graph_k;
   const u32* fwd = c->graph_shares_nbr ? c->nbr.as<u32>() : c->g_fwd.as<u32>();
   if (n_arcs) *n_arcs = arcs;
-  if (arcs >= 0xFFFFFFFFull) return ctx_fail(c, IFTWT_ERR_UNSUPPORTED, "graph too large for 32-bit CSR offsets");
+  // the segmented sort below counts its items in an int
+  if (arcs > 0x7FFFFFFFull)
+    return ctx_fail(c, IFTWT_ERR_UNSUPPORTED, "graph export is limited to 2^31 - 1 arcs (this graph has %zu)", arcs);
   ENSURE(c, c->out_a, ((size_t)n + 1) * 4 * 2);
   u32* deg_o = c->out_a.as<u32>();
   u32* off_o = deg_o + (n + 1);

@@ -329,6 +329,9 @@ __global__ void ift_resolve_kernel(u64* __restrict__ node, const u32* __restrict
 
 int ift_run(iftwt_ctx* c, const float* d_w_orig, const u32* d_seeds_orig, size_t ns) {
   if (c->graph_k == 0) return ctx_fail(c, IFTWT_ERR_STATE, "graph is not built");
+  // the buffers of the previous run are overwritten from here on: a failed call must not leave them "valid"
+  c->ift_valid = false;
+  c->rag_valid = false;
   StageTimer st(c, IFTWT_STAGE_IFT);
   const u32 n = (u32)c->n;
   ENSURE(c, c->ift_w, (size_t)n * 2 * 2 + 16);

@@ -402,7 +402,10 @@ class IFT_PCD {
     if (!idx.empty())
       s_->check(iftwt_knn_query(s_->get(), seeds->points.data(), sizeof(global::Point), idx.size(), 1, idx.data(),
                                 nullptr));
-    run(idx.data(), idx.size());
+    // NULL means "the seeds already on the device" to iftwt_ift: an empty seed cloud must not alias it
+    // (the reference with no seeds leaves every vertex at MAX_COST, ift.hpp:101)
+    static const std::int32_t none = 0;
+    run(idx.empty() ? &none : idx.data(), idx.size());
   }
   // regional-minima seeds (ift.hpp:38-44)
   explicit IFT_PCD(Graph& g) : s_(g.session()), n_(g.size()) {

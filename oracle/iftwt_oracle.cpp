@@ -484,22 +484,42 @@ ORC_API void orc_normals(const float* pts4, i64 n, const int32_t* nbr, int k, in
 // (graph builder (B), SURVEY finding 3).  Returns the arc count; adj may be
 // NULL for a counting call.
 ORC_API i64 orc_knn_graph(const int32_t* nbr, i64 n, int k, u32* off, u32* adj) {
-  std::vector<std::vector<u32>> rows((size_t)n);
+  // counting form (the vector-of-vectors form took 2.6 s per million points): every valid arc u -> v
+  // is filed under both ends, rows are sorted and de-duplicated in place, then compacted.
+  // adj == NULL: counting call, returns the arc count only (off is still filled).
+  std::vector<u64> start((size_t)n + 1, 0);
   for (i64 u = 0; u < n; ++u)
     for (int j = 0; j < k; ++j) {
       int v = nbr[u * k + j];
       if (v < 0 || v == u) continue;
-      rows[u].push_back((u32)v);
-      rows[v].push_back((u32)u);
+      ++start[(size_t)u + 1];
+      ++start[(size_t)v + 1];
     }
+  for (i64 u = 0; u < n; ++u) start[(size_t)u + 1] += start[(size_t)u];
+  std::vector<u32> raw((size_t)start[(size_t)n]);
+  {
+    std::vector<u64> cur(start.begin(), start.end() - 1);
+    for (i64 u = 0; u < n; ++u)
+      for (int j = 0; j < k; ++j) {
+        int v = nbr[u * k + j];
+        if (v < 0 || v == u) continue;
+        raw[cur[(size_t)u]++] = (u32)v;
+        raw[cur[(size_t)v]++] = (u32)u;
+      }
+  }
+  std::vector<u32> deg((size_t)n);
+#pragma omp parallel for schedule(dynamic, 4096)
+  for (i64 u = 0; u < n; ++u) {
+    u32* b = raw.data() + start[(size_t)u];
+    u32* e = raw.data() + start[(size_t)u + 1];
+    std::sort(b, e);
+    deg[(size_t)u] = (u32)(std::unique(b, e) - b);
+  }
   i64 tot = 0;
   for (i64 u = 0; u < n; ++u) {
-    auto& r = rows[u];
-    std::sort(r.begin(), r.end());
-    r.erase(std::unique(r.begin(), r.end()), r.end());
     off[u] = (u32)tot;
-    if (adj) std::copy(r.begin(), r.end(), adj + tot);
-    tot += (i64)r.size();
+    if (adj) std::copy(raw.data() + start[(size_t)u], raw.data() + start[(size_t)u] + deg[(size_t)u], adj + tot);
+    tot += (i64)deg[(size_t)u];
   }
   off[n] = (u32)tot;
   return tot;

@@ -88,10 +88,9 @@ def knn_graph(nbr):
     nbr = np.ascontiguousarray(nbr, np.int32)
     n, k = nbr.shape
     off = np.empty(n + 1, np.uint32)
-    tot = lib().orc_knn_graph(_p(nbr), C.c_int64(n), C.c_int(k), _p(off), None)
-    adj = np.empty(tot, np.uint32)
-    lib().orc_knn_graph(_p(nbr), C.c_int64(n), C.c_int(k), _p(off), _p(adj))
-    return off, adj
+    adj = np.empty(2 * n * k, np.uint32)   # upper bound: one pass instead of count + fill
+    tot = lib().orc_knn_graph(_p(nbr), C.c_int64(n), C.c_int(k), _p(off), _p(adj))
+    return off, adj[:tot].copy()
 
 
 def region_growing(nrm, nbr, theta, curv_thr=1.0, min_sz=50, max_sz=10000):

@@ -38,7 +38,9 @@ def test_example_runs_the_reference_pipeline(tmp_path):
     m = re.search(r"points (\d+)\s+vertices (\d+)\s+voxel (\S+)\s+seeds (\d+)\s+regions (\d+)", out.stdout)
     assert m, out.stdout
     assert int(m.group(1)) == 60000 and 0 < int(m.group(2)) <= 60000
-    assert int(m.group(4)) >= 1 and 1 <= int(m.group(5)) <= 10
+    # the reference's own region-growing parameters (main.cpp:112-119) on the built-in staircase: the oracle
+    # finds 23 planar patches on this scene; the labels are not vacuous
+    assert int(m.group(4)) >= 10 and 2 <= int(m.group(5)) <= 10
 
 
 def test_ply_reader_writer(tmp_path):
