@@ -44,6 +44,13 @@ WORKLOADS = {
     # segments the next cloud of the rank's share
     "cfg5": ("primitives", 2_000_000, 16, "cfg5: batch of 64 synthetic 2M-point clouds, k=16, one cloud per GPU at a time"),
 }
+# BASELINE config 4: the facade tiled 10x along x (100 M points), k = 16; k-NN + normals sharded by Morton
+# range over the ranks with an NCCL halo exchange, rows gathered to rank 0, graph / seeds / IFT there.
+# One step = one iftwt_sharded_segment over the whole cloud; total work is fixed as N grows ("strong").
+CFG4 = {"points": 100_000_000, "k": 16, "tiles": 10,
+        "desc": "cfg4: synthetic 100M-point cloud (facade tiled x10), k=16, k-NN/curvature sharded by Morton range "
+                "with NVLink halo exchange (NCCL), IFT on one GPU"}
+CFG4_PER_GPU = 12_500_000   # detail.sharded of the default line: cfg4's per-GPU share at 8 GPUs, on every N > 1
 CFG5_BATCH = 64
 THETA = 0.08  # smoothness threshold (rad) used for the synthetic scenes; see DESIGN.md
 RG_MIN, RG_MAX = 50, 10000
@@ -55,7 +62,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS) + ["cfg4"])
+    ap.add_argument("--no-sharded", action="store_true",
+                    help="N > 1: skip detail.sharded (the cfg4-style Morton-range sharded pass)")
     ap.add_argument("--points", type=int, default=0)
     ap.add_argument("--k", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=1_000_000,
@@ -212,6 +221,189 @@ class ClockSampler:
         return out
 
 
+class ShardedRun:
+    """BASELINE config 4 through the C ABI (iftwt_comm_*, iftwt_sharded_knn_normals, iftwt_sharded_segment):
+    one process per GPU, the slice of this rank resident in HBM, torch.distributed only for the barrier,
+    the max-over-ranks reductions and the 128-byte communicator id."""
+
+    def __init__(self, torch, dist, api, world, rank, local, n_total, k, tiles):
+        from iftwt_rg_b200 import sharded as host
+        self.torch, self.dist, self.api, self.host = torch, dist, api, host
+        self.world, self.rank, self.local = world, rank, local
+        self.n_total, self.k = n_total, k
+        self.lo, self.hi = host.slice_bounds(n_total, world, rank)
+        # generation order is random in space, so a contiguous id range is a uniform subsample of 1-2 tiles
+        self.host_pts = torch.from_numpy(synth.facade_tiled(n_total, tiles=tiles, start=self.lo,
+                                                            count=self.hi - self.lo)).pin_memory()
+        self.dev_pts = self.host_pts.cuda()
+        torch.cuda.synchronize()
+        self.comm = host.make_comm(local)
+        self.ctx = self.comm.ctx(0)
+        self.stream = torch.cuda.ExternalStream(self.ctx.stream(), device=torch.device("cuda", local))
+        self.rg = api.RgParams(RG_MIN, RG_MAX, k, THETA, 1.0)
+        self.radius = 0.0
+
+    def slices(self):
+        return [(self.dev_pts.data_ptr(), self.hi - self.lo, self.lo)]
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, vals, op):
+        t = self.torch.tensor(vals, device="cuda", dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=op)
+        return [float(x) for x in t.tolist()]
+
+    def timed(self, fn, steps=1):
+        """CUDA events on the shard's stream around `steps` calls, max over ranks (ms)."""
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record(self.stream)
+        r = None
+        for _ in range(steps):
+            r = fn()
+        e1.record(self.stream)
+        self.barrier()
+        return self.reduce([e0.elapsed_time(e1)], self.dist.ReduceOp.MAX)[0], r
+
+    def knn_normals(self, radius):
+        return self.comm.sharded_knn_normals(self.slices(), self.k, True, radius)[0]
+
+    def segment(self, download=False):
+        return self.comm.sharded_segment(self.slices(), self.k, self.rg, root=0, halo_radius=self.radius,
+                                         n_total=self.n_total, download=download)
+
+    def warm(self):
+        """First call: allocations, NCCL channels, and the halo-radius estimate.  Later calls pass a little
+        more than the largest k-th neighbour distance the first one measured — what a caller that segments
+        similar clouds repeatedly does (iftwt.h: iftwt_shard_out.kth_distance_max)."""
+        ms, o = self.timed(lambda: self.knn_normals(0.0))
+        self.first = {"ms": ms, "attempts": o.attempts, "estimated_radius": o.halo_radius,
+                      "kth_distance_max": o.kth_distance_max}
+        self.radius = 1.05 * o.kth_distance_max
+        return o
+
+    def phase_stats(self, o):
+        dist = self.dist
+        mx = self.reduce([o.ms_estimate, o.ms_partition, o.ms_exchange, o.ms_compute, o.ms_export, o.knn_cell_ms],
+                         dist.ReduceOp.MAX)
+        sm = self.reduce([float(o.halo_bytes_sent), float(o.exchange_bytes_sent), float(o.n_owned), float(o.n_halo)],
+                         dist.ReduceOp.SUM)
+        per = self.torch.zeros(self.world * 2, device="cuda", dtype=self.torch.float64)
+        per[2 * self.rank], per[2 * self.rank + 1] = float(o.n_owned), float(o.n_halo)
+        if self.world > 1:
+            dist.all_reduce(per)
+        per = [int(x) for x in per.tolist()]
+        return {"phase_ms_max_over_ranks": {"estimate": mx[0], "partition_route_pack": mx[1], "nccl_exchange": mx[2],
+                                            "grid_knn_normals": mx[3], "export_rows_and_check": mx[4],
+                                            "knn_cell_kernel": mx[5]},
+                "halo_bytes_over_nvlink": int(sm[0]), "exchange_bytes_over_nvlink": int(sm[1]),
+                "owned_per_rank": per[0::2], "halo_per_rank": per[1::2], "halo_fraction": sm[3] / max(sm[2], 1.0),
+                "halo_radius": o.halo_radius, "attempts": o.attempts}
+
+    def verify(self, o, target_rows=1_000_000):
+        """A sample of every rank's rows against ONE GPU holding the whole cloud: rank 0 answers the sampled
+        points as external queries (the general k-NN path, not the code that produced the rows)."""
+        torch, dist = self.torch, self.dist
+        dev = torch.device("cuda", self.local)
+        v = self.host.as_torch(o, self.local)
+        stride = max(1, self.n_total // target_rows)
+        sel = slice(0, None, stride)
+        if o.n_owned:
+            gid, knn, d2 = v["gid"][sel].clone(), v["knn"][sel].clone(), v["d2"][sel].clone()
+        else:
+            gid = torch.zeros(0, dtype=torch.uint32, device=dev)
+            knn = torch.zeros((0, self.k), dtype=torch.int32, device=dev)
+            d2 = torch.zeros((0, self.k), dtype=torch.float32, device=dev)
+        torch.cuda.synchronize()
+        if self.world > 1:
+            per = (self.n_total + self.world - 1) // self.world
+            cap = (per + 2 * self.world) // stride + 4096   # owned counts are balanced to a bin, not exactly
+            cnt = torch.tensor([gid.shape[0]], device=dev, dtype=torch.int64)
+            mx = cnt.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            cap = max(cap, int(mx))
+            def pad(t, shape, dtype):
+                out = torch.zeros(shape, dtype=dtype, device=dev)
+                out[: t.shape[0]] = t
+                return out
+            g_all = [torch.empty(cap, dtype=torch.int32, device=dev) for _ in range(self.world)]
+            k_all = [torch.empty((cap, self.k), dtype=torch.int32, device=dev) for _ in range(self.world)]
+            d_all = [torch.empty((cap, self.k), dtype=torch.float32, device=dev) for _ in range(self.world)]
+            c_all = [torch.empty(1, dtype=torch.int64, device=dev) for _ in range(self.world)]
+            dist.all_gather(g_all, pad(gid.view(torch.int32), (cap,), torch.int32))
+            dist.all_gather(k_all, pad(knn, (cap, self.k), torch.int32))
+            dist.all_gather(d_all, pad(d2, (cap, self.k), torch.float32))
+            dist.all_gather(c_all, cnt)
+            # the whole cloud on every rank (only rank 0 uses it): slices padded to one size
+            slab = torch.zeros((per, 4), dtype=torch.float32, device=dev)
+            slab[: self.hi - self.lo] = self.dev_pts
+            s_all = [torch.empty_like(slab) for _ in range(self.world)]
+            dist.all_gather(s_all, slab)
+            if self.rank != 0:
+                return None
+            whole = torch.cat([s_all[r][: self.host.slice_bounds(self.n_total, self.world, r)[1] -
+                                        self.host.slice_bounds(self.n_total, self.world, r)[0]] for r in range(self.world)])
+            gid = torch.cat([g_all[r][: int(c_all[r])] for r in range(self.world)])
+            knn = torch.cat([k_all[r][: int(c_all[r])] for r in range(self.world)])
+            d2 = torch.cat([d_all[r][: int(c_all[r])] for r in range(self.world)])
+            del s_all, g_all, k_all, d_all
+        else:
+            whole = self.dev_pts
+            gid = gid.view(torch.int32)
+        q = whole[gid.long(), :3].cpu().numpy()
+        torch.cuda.synchronize()
+        with self.api.Context(self.local) as c1:
+            c1.set_cloud_device(whole.data_ptr(), self.n_total)
+            ridx, rd2 = c1.knn_query(q, self.k)
+        ok = bool(np.array_equal(ridx, knn.cpu().numpy()) and
+                  np.array_equal(rd2.view(np.uint32), d2.cpu().numpy().view(np.uint32)))
+        return {"verify_rows_equal": ok, "verified_rows": int(len(q)),
+                "verified_against": "one GPU holding the whole cloud, general k-NN path (iftwt_knn_query)"}
+
+    def close(self):
+        self.comm.close()
+
+
+def sharded_detail(args, torch, dist, api, world, rank, local, n_total, k, tiles, steps):
+    """The cfg4-shaped pass reported as detail.sharded in the default line when N > 1."""
+    run = ShardedRun(torch, dist, api, world, rank, local, n_total, k, tiles)
+    try:
+        run.warm()
+        ms, o = run.timed(lambda: run.knn_normals(run.radius), steps)
+        ms /= steps
+        out = {"workload": f"cfg4-shaped: facade tiled, {n_total} points over {world} GPUs "
+                           f"({(n_total + world - 1) // world} per GPU), k={k}; slices resident in HBM",
+               "what": "iftwt_sharded_knn_normals: Morton-range partition, owner + halo exchange (grouped ncclSend/"
+                       "ncclRecv), grid + k-NN + normals on owned + halo points, rows exported with global ids",
+               "points": n_total, "k": k, "n_gpus": world, "steps": steps, "knn_normals_ms": ms,
+               "knn_normals_points_per_s": n_total / (ms * 1e-3), "first_call": run.first}
+        out.update(run.phase_stats(o))
+        alg = (16 + 4 * k + 16) * n_total      # fused k-NN + curvature figure of SURVEY 8(d)
+        out["algorithmic_gbs_all_gpus"] = alg / (ms * 1e-3) / 1e9
+        ver = run.verify(o)
+        if ver:
+            out.update(ver)
+        run.segment()                                   # warm-up: allocations on the root
+        ms_seg, res = run.timed(lambda: run.segment())
+        st = run.ctx.stats() if rank == 0 else {}
+        out["segment_ms"] = ms_seg
+        out["segment_points_per_s"] = n_total / (ms_seg * 1e-3)
+        out["segment_what"] = "iftwt_sharded_segment: the above + rows gathered to rank 0 (NCCL), graph / seeds / IFT there"
+        if rank == 0:
+            out["segment_seeds"] = int(res[2])
+            out["segment_root_stage_ms"] = {s: v for s, v in run.ctx.stage_ms().items()
+                                            if s in ("grid", "graph", "graph_rg", "seeds", "ift")}
+            out["segment_stats"] = {kk: st[kk] for kk in ("n_arcs", "n_seeds", "ift_levels")}
+        return out
+    finally:
+        run.close()
+
+
 def reference_arm(args, gen, n_full, k, desc):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -321,6 +513,13 @@ def emit(line: dict):
 def main():
     args = parse()
     quiet_stdout()
+    if args.workload == "cfg4":
+        if args.impl == "reference":
+            # the CPU arm of config 4 is the same pipeline on the same scene: a slab of one tile
+            reference_arm(args, "facade", 10_000_000, args.k or CFG4["k"], CFG4["desc"])
+            return
+        main_cfg4(args)
+        return
     gen, n_default, k_default, desc = WORKLOADS[args.workload]
     n = args.points or n_default
     k = args.k or k_default
@@ -549,8 +748,121 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu, "detail": extra,
         }
-        emit(line)
     ctx.close()
+    if world > 1 and not args.no_sharded and args.workload == "cfg3":
+        # BASELINE config 4's shape on the same GPUs: k-NN + normals sharded by Morton range with an NCCL halo
+        # exchange, inside the library.  A collective that hangs must not cost the line above: a watchdog on
+        # every rank lets rank 0 print what it has and ends the process.
+        import threading as _th
+
+        def _bail():
+            if rank == 0:
+                line["detail"]["sharded"] = {"error": "timed out after 240 s"}
+                emit(line)
+            os._exit(0)
+
+        wd = _th.Timer(240.0, _bail)
+        wd.daemon = True
+        wd.start()
+        try:
+            sh = sharded_detail(args, torch, dist, api, world, rank, local, CFG4_PER_GPU * world, CFG4["k"],
+                                max(1, round(CFG4_PER_GPU * world / 10_000_000)), steps=5)
+        except Exception as e:
+            sh = {"error": repr(e)[:400]}
+        wd.cancel()
+        if rank == 0:
+            line["detail"]["sharded"] = sh
+    if rank == 0:
+        emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main_cfg4(args):
+    """--workload cfg4: a step = one iftwt_sharded_segment over the whole 100 M-point cloud."""
+    import torch
+    import torch.distributed as dist
+    from iftwt_rg_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_total = args.points or CFG4["points"]
+    k = args.k or CFG4["k"]
+    tiles = max(1, round(n_total / 10_000_000))
+    run = ShardedRun(torch, dist, api, world, rank, local, n_total, k, tiles)
+    o = run.warm()
+    for _ in range(max(args.warmup, 3) - 1):
+        run.knn_normals(run.radius)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_knn, o = run.timed(lambda: run.knn_normals(run.radius), args.steps)
+    ms_knn /= args.steps
+    phases = run.phase_stats(o)
+    ver = run.verify(o)
+    run.segment()
+    run.segment()
+    run.ctx.reset_counters()
+    ms_seg, res = run.timed(lambda: run.segment(), args.steps)
+    clocks = sampler.stop() if rank == 0 else {}
+    launches = run.reduce([float(run.ctx.stats()["kernel_launches"])], dist.ReduceOp.SUM)[0]
+    root_stage = run.ctx.stage_ms() if rank == 0 else {}
+    root_stats = run.ctx.stats() if rank == 0 else {}
+    e2e = None
+    if not args.no_e2e:
+        # slices from pinned host memory every step, cost + label of the whole cloud back to the host on rank 0
+        def step_e2e():
+            with torch.cuda.stream(run.stream):
+                run.dev_pts.copy_(run.host_pts, non_blocking=True)
+            return run.segment(download=True)
+        step_e2e()
+        ms_e2e, _ = run.timed(step_e2e, args.steps)
+        e2e = {"value": n_total * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(n_total * 16),
+               "d2h_bytes_per_step": int(n_total * 8), "ms_per_step": ms_e2e / args.steps,
+               "note": "every rank uploads its slice from pinned memory; rank 0 downloads cost + label of all points "
+                       "(pageable numpy buffers allocated per call)"}
+    if rank == 0:
+        peaks, which = {}, "fallback"
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            which = "measured"
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        cell_ms = phases["phase_ms_max_over_ranks"]["knn_cell_kernel"]
+        per_gpu = (n_total + world - 1) // world
+        alg = (16 + 4 * k) * per_gpu
+        ach = alg / (cell_ms * 1e-3) / 1e9 if cell_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": n_total * args.steps / (ms_seg * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_seg / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
+            "config": {"workload": CFG4["desc"] if n_total == CFG4["points"] and k == CFG4["k"] else
+                       f"facade tiled n={n_total} k={k}", "k": k, "points": n_total,
+                       "parallelism": f"k-NN + normals sharded by Morton range over {world} GPUs (NCCL halo exchange), "
+                                      "rows gathered to rank 0, graph / seeds / IFT on rank 0",
+                       "l2": "every slice (>= 200 MB) and every intermediate exceed the 126 MB L2"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "knn_cell_kernel on the slowest shard (owned + halo points)",
+                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if peak else None,
+                         "traffic": None, "peak_source": which, "algorithmic_bytes_per_launch": alg,
+                         "avg_launch_ms": cell_ms,
+                         "active_limiter": "instruction issue, not HBM (see the cfg3 line and profiles/)"},
+            "cpu_baseline": None,
+            "detail": {"sharded_knn_normals": dict({"ms": ms_knn, "points_per_s": n_total / (ms_knn * 1e-3),
+                                                    "first_call": run.first}, **phases, **(ver or {})),
+                       "root_stage_ms": root_stage,
+                       "root_stats": {kk: root_stats[kk] for kk in ("n_arcs", "n_seeds", "ift_levels", "rg_segments")},
+                       "seeds": int(res[2])},
+        }
+        emit(line)
+    run.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -12,7 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libiftwt.so")
-SOURCES = ["grid.cu", "knn.cu", "graph.cu", "normals.cu", "seeds.cu", "ift.cu", "voxel.cu", "hierarchy.cu", "capi.cu"]
+SOURCES = ["grid.cu", "knn.cu", "graph.cu", "normals.cu", "seeds.cu", "ift.cu", "voxel.cu", "hierarchy.cu", "shard.cu",
+           "capi.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

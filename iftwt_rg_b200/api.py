@@ -51,6 +51,27 @@ class Stats(C.Structure):
         return {f: getattr(self, f) for f, _ in self._fields_}
 
 
+class ShardIn(C.Structure):
+    """A rank's slice of the cloud (include/iftwt.h: iftwt_shard_in)."""
+    _fields_ = [("d_points", C.c_void_p), ("n", C.c_size_t), ("gid0", C.c_uint64)]
+
+
+class ShardOut(C.Structure):
+    """include/iftwt.h: iftwt_shard_out.  Device pointers are owned by the comm."""
+    _fields_ = [("n_owned", C.c_size_t), ("n_halo", C.c_size_t), ("n_total", C.c_size_t), ("k", C.c_int),
+                ("attempts", C.c_int), ("d_gid", C.c_void_p), ("d_points", C.c_void_p), ("d_knn", C.c_void_p),
+                ("d_d2", C.c_void_p), ("d_normals", C.c_void_p), ("halo_radius", C.c_double),
+                ("kth_distance_max", C.c_double), ("halo_bytes_sent", C.c_uint64),
+                ("exchange_bytes_sent", C.c_uint64), ("ms_estimate", C.c_float), ("ms_partition", C.c_float),
+                ("ms_exchange", C.c_float), ("ms_compute", C.c_float), ("ms_export", C.c_float),
+                ("knn_cell_ms", C.c_float)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_ if not f.startswith("d_")}
+
+
+COMM_ID_BYTES = 128
+
 _lib = None
 
 
@@ -106,6 +127,19 @@ def load_library(build_if_missing: bool = True):
     lib.iftwt_synchronize.argtypes = [vp]
     lib.iftwt_stream.argtypes = [vp]
     lib.iftwt_stream.restype = vp
+    lib.iftwt_comm_unique_id.argtypes = [vp]
+    lib.iftwt_comm_create.argtypes = [C.POINTER(vp), vp, i32, i32, i32]
+    lib.iftwt_comm_create_all.argtypes = [C.POINTER(vp), i32, C.POINTER(i32)]
+    lib.iftwt_comm_destroy.argtypes = [vp]
+    lib.iftwt_comm_destroy.restype = None
+    lib.iftwt_comm_last_error.argtypes = [vp]
+    lib.iftwt_comm_last_error.restype = C.c_char_p
+    lib.iftwt_comm_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    lib.iftwt_comm_ctx.argtypes = [vp, i32]
+    lib.iftwt_comm_ctx.restype = vp
+    lib.iftwt_sharded_knn_normals.argtypes = [vp, C.POINTER(ShardIn), i32, i32, C.c_double, C.POINTER(ShardOut)]
+    lib.iftwt_sharded_segment.argtypes = [vp, C.POINTER(ShardIn), C.POINTER(SegmentParams), C.c_double, i32, vp, vp,
+                                          C.POINTER(sz), C.POINTER(ShardOut)]
     _lib = lib
     return lib
 
@@ -117,8 +151,13 @@ def _ptr(a):
 class Context:
     """One ctx = one GPU, one stream (include/iftwt.h)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, _borrowed=None):
         self._lib = load_library()
+        self._owned = _borrowed is None
+        if _borrowed is not None:  # a ctx that belongs to a Comm (iftwt_comm_ctx)
+            self._h = C.c_void_p(_borrowed)
+            self.n = 0
+            return
         h = C.c_void_p()
         rc = self._lib.iftwt_create(C.byref(h), device)
         if rc != 0:
@@ -128,7 +167,8 @@ class Context:
 
     def close(self):
         if getattr(self, "_h", None):
-            self._lib.iftwt_destroy(self._h)
+            if self._owned:
+                self._lib.iftwt_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -354,3 +394,126 @@ class Context:
 
     def stream(self) -> int:
         return int(self._lib.iftwt_stream(self._h) or 0)
+
+
+class DeviceArray:
+    """A device buffer owned by the library, seen through __cuda_array_interface__ (zero copy:
+    torch.as_tensor(x, device="cuda") / cupy.asarray(x) wrap it without moving data)."""
+
+    def __init__(self, ptr: int, shape: tuple, typestr: str, owner=None):
+        self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": typestr,
+                                         "data": (int(ptr or 0), False), "version": 2, "strides": None}
+        self._owner = owner
+
+
+class Comm:
+    """Morton-range sharded k-NN / normals over the GPUs of one node (include/iftwt.h, csrc/shard.cu).
+
+    Comm.rank(id, nranks, rank, device): one process per GPU (ncclCommInitRank); the id comes from
+    Comm.unique_id() on rank 0 and travels over any side channel.
+    Comm.all(devices): one process driving several GPUs (ncclCommInitAll); the same device named several
+    times = shards time-sharing one GPU (the single-GPU test mode)."""
+
+    def __init__(self, handle, nlocal):
+        self._lib = load_library()
+        self._h = handle
+        self.n_local = nlocal
+
+    @staticmethod
+    def unique_id() -> bytes:
+        lib = load_library()
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        rc = lib.iftwt_comm_unique_id(buf)
+        if rc != 0:
+            raise IftwtError(rc, lib.iftwt_comm_last_error(None).decode())
+        return buf.raw
+
+    @classmethod
+    def rank(cls, uid: bytes, nranks: int, rank: int, device: int) -> "Comm":
+        lib = load_library()
+        h = C.c_void_p()
+        buf = C.create_string_buffer(bytes(uid), COMM_ID_BYTES)
+        rc = lib.iftwt_comm_create(C.byref(h), buf, nranks, rank, device)
+        if rc != 0:
+            raise IftwtError(rc, lib.iftwt_comm_last_error(None).decode())
+        return cls(h, 1)
+
+    @classmethod
+    def all(cls, devices) -> "Comm":
+        lib = load_library()
+        h = C.c_void_p()
+        arr = (C.c_int * len(devices))(*devices)
+        rc = lib.iftwt_comm_create_all(C.byref(h), len(devices), arr)
+        if rc != 0:
+            raise IftwtError(rc, lib.iftwt_comm_last_error(None).decode())
+        return cls(h, len(devices))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.iftwt_comm_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise IftwtError(rc, self._lib.iftwt_comm_last_error(self._h).decode())
+
+    def info(self):
+        a, b, c = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._check(self._lib.iftwt_comm_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"nranks": a.value, "n_local": b.value, "first_local_rank": c.value}
+
+    def ctx(self, local_index: int = 0) -> Context:
+        h = self._lib.iftwt_comm_ctx(self._h, local_index)
+        if not h:
+            raise IftwtError(-1, "no such local shard")
+        return Context(_borrowed=h)
+
+    def _ins(self, slices):
+        """slices: one (device_ptr, n, gid0) per local shard."""
+        assert len(slices) == self.n_local
+        return (ShardIn * self.n_local)(*[ShardIn(C.c_void_p(int(p) or None), int(n), int(g)) for p, n, g in slices])
+
+    def sharded_knn_normals(self, slices, k: int, want_normals: bool = True, halo_radius: float = 0.0):
+        ins = self._ins(slices)
+        outs = (ShardOut * self.n_local)()
+        self._check(self._lib.iftwt_sharded_knn_normals(self._h, ins, k, 1 if want_normals else 0,
+                                                        float(halo_radius), outs))
+        return list(outs)
+
+    def sharded_segment(self, slices, k: int, rg: RgParams, root: int = 0, halo_radius: float = 0.0,
+                        n_total: int | None = None, download: bool = True, gradient_weights: bool = False):
+        """BASELINE config 4.  Returns (cost, label, n_seeds, outs); cost / label are None unless this
+        process holds `root`, downloads and knows n_total."""
+        ins = self._ins(slices)
+        outs = (ShardOut * self.n_local)()
+        p = SegmentParams(k, k, rg, 1 if gradient_weights else 0)
+        ns = C.c_size_t(0)
+        info = self.info()
+        holds_root = info["first_local_rank"] <= root < info["first_local_rank"] + info["n_local"]
+        cost = label = None
+        if download and holds_root and n_total:
+            cost = np.empty(n_total, np.uint32)
+            label = np.empty(n_total, np.uint32)
+        self._check(self._lib.iftwt_sharded_segment(self._h, ins, C.byref(p), float(halo_radius), root, _ptr(cost),
+                                                    _ptr(label), C.byref(ns), outs))
+        return cost, label, ns.value, list(outs)
+
+    @staticmethod
+    def arrays(o: ShardOut):
+        """The device-resident result of one shard as __cuda_array_interface__ objects."""
+        n, k = o.n_owned, o.k
+        return {"gid": DeviceArray(o.d_gid, (n,), "<u4"), "points": DeviceArray(o.d_points, (n, 4), "<f4"),
+                "knn": DeviceArray(o.d_knn, (n, k), "<i4"), "d2": DeviceArray(o.d_d2, (n, k), "<f4"),
+                "normals": DeviceArray(o.d_normals, (n, 4), "<f4") if o.d_normals else None}

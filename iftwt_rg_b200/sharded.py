@@ -1,248 +1,58 @@
-"""Morton-range sharded k-NN / normals across the GPUs of one node (BASELINE config 4).
+"""Host side of the sharded path in the one-process-per-GPU mode (torchrun): slice bookkeeping, the
+hand-over of the NCCL unique id, and zero-copy torch views of the device-resident results.
 
-One process per GPU (torchrun), `torch.distributed` for the plumbing, libiftwt.so for every
-kernel.  The path has exactly one exchange step before the compute and none during it
-(SURVEY 8(e)):
-
-  1. global bounding box                                 all_reduce MIN / MAX   (6 floats)
-  2. coarse grid of side `s` (the halo radius), Morton key per point, histogram of the key's
-     top bits                                            all_reduce SUM   (<= 2^18 bins)
-     -> contiguous, balanced Morton ranges, one per rank
-  3. every point goes to the rank that owns its range    all_to_all (counts, then payload)
-  4. halo: a point is also sent to every other rank that owns one of the 26 coarse cells around
-     its own                                             all_to_all (counts, then payload)
-  5. each rank runs the single-GPU k-NN / normals on owned + halo points and keeps the rows of
-     the points it owns, translated to global ids.
-
-Exactness: every point within `s` of an owned point p lies in the 3x3x3 coarse block around
-p's cell, and that whole block is present on p's owner (owned or halo).  So the rows are the
-exact global k-NN iff every owned point's k-th distance is <= s; this is checked after the
-fact (all_reduce MAX) and the exchange is redone with 2s when it fails.
-
-The IFT itself does not shard (global ordered propagation: replicas only).  For config 4 the
-rows are gathered to rank 0 and installed with `iftwt_set_knn_rows_device`.
-
-The partition / halo logic is plain torch and runs unchanged on CPU tensors with the gloo
-backend, which is how tests/test_sharded_gloo.py exercises it (the oracle standing in for the
-GPU kernels through the `local_knn` hook).
+Everything that touches the data — partition, owner routing, halo selection, the NCCL exchange, the
+k-NN / normals kernels, the row export, the gather to the IFT rank — lives in libiftwt.so
+(csrc/shard.cu: iftwt_comm_*, iftwt_sharded_knn_normals, iftwt_sharded_segment).  `torch.distributed`
+is the side channel for 128 bytes and nothing else.
 """
 from __future__ import annotations
 
-import math
-from dataclasses import dataclass, field
-
-import numpy as np
 import torch
 import torch.distributed as dist
 
-
-def _spread10(v: torch.Tensor) -> torch.Tensor:
-    v = v & 0x3FF
-    v = (v | (v << 16)) & 0x030000FF
-    v = (v | (v << 8)) & 0x0300F00F
-    v = (v | (v << 4)) & 0x030C30C3
-    v = (v | (v << 2)) & 0x09249249
-    return v
+from . import api
 
 
-def morton30(ix: torch.Tensor, iy: torch.Tensor, iz: torch.Tensor) -> torch.Tensor:
-    """x is the most significant axis bit of every triple (same convention as the kernels)."""
-    return (_spread10(ix) << 2) | (_spread10(iy) << 1) | _spread10(iz)
+def slice_bounds(n_total: int, world: int, rank: int) -> tuple[int, int]:
+    """[lo, hi) of rank's slice: consecutive global-id ranges, ascending with the rank, covering
+    0 .. n_total (what iftwt_shard_in asks for)."""
+    return rank * n_total // world, (rank + 1) * n_total // world
 
 
-@dataclass
-class Partition:
-    origin: torch.Tensor          # (3,) float64 global bbox min
-    cell: float                   # coarse cell side = halo radius
-    dims: tuple                   # coarse grid dims
-    shift: int                    # histogram bin = key >> shift
-    owner_of_bin: torch.Tensor    # (nbins,) int64
-
-    def cells(self, xyz: torch.Tensor):
-        c = torch.floor((xyz.double() - self.origin) / self.cell).long()
-        for a in range(3):
-            c[:, a].clamp_(0, self.dims[a] - 1)
-        return c
-
-    def owner_of_cells(self, c: torch.Tensor) -> torch.Tensor:
-        key = morton30(c[:, 0], c[:, 1], c[:, 2])
-        return self.owner_of_bin[key >> self.shift]
+def broadcast_id(uid: bytes | None, src: int = 0, group=None) -> bytes:
+    """Rank `src` passes the id it got from Comm.unique_id(); every rank returns it.  Works on any
+    backend (a CPU tensor under gloo, a CUDA tensor under nccl)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        assert uid is not None
+        return bytes(uid)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    t = torch.zeros(api.COMM_ID_BYTES, dtype=torch.uint8)
+    if dist.get_rank(group) == src:
+        assert uid is not None and len(uid) == api.COMM_ID_BYTES
+        t = torch.frombuffer(bytearray(uid), dtype=torch.uint8).clone()
+    t = t.to(dev)
+    dist.broadcast(t, src=src, group=group)
+    return bytes(t.cpu().numpy().tobytes())
 
 
-def _all_reduce(t, op, group):
-    if dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(t, op=op, group=group)
-    return t
-
-
-def make_partition(xyz: torch.Tensor, cell: float, world: int, group=None) -> Partition:
-    dev = xyz.device
-    lo = xyz.min(dim=0).values.float() if len(xyz) else torch.full((3,), float("inf"), device=dev)
-    hi = xyz.max(dim=0).values.float() if len(xyz) else torch.full((3,), float("-inf"), device=dev)
-    _all_reduce(lo, dist.ReduceOp.MIN, group)
-    _all_reduce(hi, dist.ReduceOp.MAX, group)
-    ext = (hi - lo).double().clamp_min(1e-30)
-    # at most 1024 cells per axis: a coarser grid only makes the halo thicker, never wrong
-    cell = max(float(cell), float(ext.max()) / 1023.0)
-    dims = tuple(int(math.floor(float(e) / cell)) + 1 for e in ext)
-    bits = max(1, max(int(math.ceil(math.log2(max(d, 2)))) for d in dims))
-    shift = max(0, 3 * bits - 18)
-    nbins = 1 << (3 * bits - shift)
-    part = Partition(lo.double(), cell, dims, shift, torch.zeros(nbins, dtype=torch.long, device=dev))
-    c = part.cells(xyz)
-    key = morton30(c[:, 0], c[:, 1], c[:, 2])
-    hist = torch.bincount(key >> shift, minlength=nbins).to(torch.int64)
-    _all_reduce(hist, dist.ReduceOp.SUM, group)
-    cum = torch.cumsum(hist, 0)
-    total = int(cum[-1])
-    # bin b goes to rank floor(points_before_b * world / total): contiguous Morton ranges
-    before = cum - hist
-    part.owner_of_bin = torch.clamp((before * world) // max(total, 1), max=world - 1)
-    return part
-
-
-def _exchange(payloads, dest: torch.Tensor, world: int, group=None):
-    """Send row i of every payload to rank dest[i]; returns the received payloads (ordered by
-    source rank, then by the sender's order) ."""
+def make_comm(device: int, group=None) -> api.Comm:
+    """The comm of this process (one GPU): ncclGetUniqueId on rank 0, ncclCommInitRank everywhere."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
     if world == 1:
-        return [p.clone() for p in payloads]
-    order = torch.argsort(dest, stable=True)
-    counts = torch.bincount(dest, minlength=world).to(torch.int64)
-    recv_counts = torch.empty_like(counts)
-    dist.all_to_all_single(recv_counts, counts, group=group)
-    out = []
-    send_split = counts.tolist()
-    recv_split = recv_counts.tolist()
-    for p in payloads:
-        src = p[order].contiguous()
-        dst = torch.empty((sum(recv_split),) + tuple(p.shape[1:]), dtype=p.dtype, device=p.device)
-        dist.all_to_all_single(dst, src, output_split_sizes=recv_split, input_split_sizes=send_split, group=group)
-        out.append(dst)
-    return out
+        return api.Comm.all([device])
+    uid = api.Comm.unique_id() if rank == 0 else None
+    return api.Comm.rank(broadcast_id(uid, 0, group), world, rank, device)
 
 
-def halo_destinations(part: Partition, xyz: torch.Tensor, rank: int, world: int):
-    """(point index, destination rank) pairs: ranks other than `rank` owning one of the 26
-    coarse cells around each point's own cell."""
-    c = part.cells(xyz)
-    m = len(xyz)
-    need = torch.zeros((m, world), dtype=torch.bool, device=xyz.device)
-    dims = torch.tensor(part.dims, device=xyz.device)
-    for dx in (-1, 0, 1):
-        for dy in (-1, 0, 1):
-            for dz in (-1, 0, 1):
-                if dx == dy == dz == 0:
-                    continue
-                n = c + torch.tensor([dx, dy, dz], device=xyz.device)
-                ok = ((n >= 0) & (n < dims)).all(dim=1)
-                own = part.owner_of_cells(torch.where(ok[:, None], n, c))
-                need[torch.arange(m, device=xyz.device)[ok], own[ok]] = True
-    need[:, rank] = False
-    idx, dst = torch.nonzero(need, as_tuple=True)
-    return idx, dst
-
-
-@dataclass
-class ShardResult:
-    gid: torch.Tensor            # (m,) global ids of the owned points
-    pts: torch.Tensor            # (m, 4) owned points
-    knn_gid: torch.Tensor        # (m, k) global ids of the neighbours, canonical order
-    d2: torch.Tensor             # (m, k)
-    normals: torch.Tensor | None  # (m, 4) {nx,ny,nz,curvature}
-    stats: dict = field(default_factory=dict)
-
-
-def gpu_local_knn(ctx):
-    """local_knn hook backed by libiftwt.so on the rank's GPU."""
-    def run(local_pts: torch.Tensor, k: int, want_normals: bool):
-        n = local_pts.shape[0]
-        # the ctx runs on its own stream: everything torch queued for these tensors must be done
-        torch.cuda.current_stream(local_pts.device).synchronize()
-        ctx.set_cloud_device(local_pts.data_ptr(), n)
-        idx = torch.empty((n, k), dtype=torch.int32, device=local_pts.device)
-        d2 = torch.empty((n, k), dtype=torch.float32, device=local_pts.device)
-        ctx.knn_device(k, idx.data_ptr(), d2.data_ptr())
-        nrm = None
-        if want_normals:
-            nrm = torch.empty((n, 4), dtype=torch.float32, device=local_pts.device)
-            ctx.normals_device(k, nrm.data_ptr())
-        return idx, d2, nrm
-    return run
-
-
-def sharded_knn(local_pts: torch.Tensor, gid0: int, k: int, local_knn, halo_radius: float,
-                want_normals: bool = True, group=None, max_retries: int = 10) -> ShardResult:
-    """local_pts: (m, 4) float32 {x,y,z,intensity} slice held by this rank, global ids
-    gid0 .. gid0+m-1.  Returns the exact global k-NN rows (and normals) of the points this rank
-    ends up owning."""
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
-    dev = local_pts.device
-    gid = gid0 + torch.arange(local_pts.shape[0], device=dev, dtype=torch.int64)
-    s = float(halo_radius)
-    for attempt in range(max_retries + 1):
-        part = make_partition(local_pts[:, :3], s, world, group)
-        owner = part.owner_of_cells(part.cells(local_pts[:, :3]))
-        own_pts, own_gid = _exchange([local_pts, gid], owner, world, group)
-        h_idx, h_dst = halo_destinations(part, own_pts[:, :3], rank, world)
-        halo_pts, halo_gid = _exchange([own_pts[h_idx], own_gid[h_idx]], h_dst, world, group)
-        m = own_pts.shape[0]
-        cloud = torch.cat([own_pts, halo_pts], 0).contiguous()
-        cloud_gid = torch.cat([own_gid, halo_gid], 0)
-        # ties are broken by index: make the LOCAL index order agree with the GLOBAL id order
-        order = torch.argsort(cloud_gid, stable=True)
-        inv_order = torch.empty_like(order)
-        inv_order[order] = torch.arange(len(order), device=dev)
-        cloud_s = cloud[order].contiguous()
-        gid_s = cloud_gid[order]
-        idx, d2, nrm = local_knn(cloud_s, k, want_normals)
-        rows = inv_order[:m]                                   # local position of each owned point
-        idx_o = idx[rows].long()
-        d2_o = d2[rows]
-        knn_gid = torch.where(idx_o >= 0, gid_s[idx_o.clamp_min(0)], torch.full_like(idx_o, -1))
-        # exactness check: k-th distance inside the halo radius (inf rows = fewer than k points overall)
-        kth = d2_o[:, k - 1]
-        finite = torch.isfinite(kth)
-        viol = torch.tensor([int(((kth > part.cell * part.cell) & finite).sum())], device=dev, dtype=torch.int64)
-        _all_reduce(viol, dist.ReduceOp.SUM, group)
-        if int(viol) == 0:
-            stats = {"rank": rank, "owned": int(m), "halo": int(halo_pts.shape[0]), "halo_radius": part.cell,
-                     "attempts": attempt + 1, "violations": int(viol)}
-            return ShardResult(own_gid, own_pts, knn_gid, d2_o, None if nrm is None else nrm[rows], stats)
-        s = 2.0 * part.cell
-    raise RuntimeError(f"sharded k-NN: halo radius still too small after {max_retries + 1} exchanges "
-                       f"({int(viol)} owned points with a k-th neighbour beyond {part.cell:g})")
-
-
-def gather_rows_to_rank0(res: ShardResult, n_total: int, k: int, group=None):
-    """Rows of every rank, scattered to global-id order on rank 0 (config 4: the IFT runs on
-    one GPU).  Returns (pts, knn_gid int32, d2) on rank 0, None elsewhere."""
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
-    dev = res.gid.device
-    dest = torch.zeros(len(res.gid), dtype=torch.int64, device=dev)
-    gid, pts, knn, d2 = _exchange([res.gid, res.pts, res.knn_gid.int(), res.d2], dest, world, group)
-    if rank != 0:
-        return None
-    out_pts = torch.empty((n_total, 4), dtype=torch.float32, device=dev)
-    out_idx = torch.empty((n_total, k), dtype=torch.int32, device=dev)
-    out_d2 = torch.empty((n_total, k), dtype=torch.float32, device=dev)
-    out_pts[gid] = pts
-    out_idx[gid] = knn
-    out_d2[gid] = d2
-    return out_pts, out_idx, out_d2
-
-
-def estimate_halo_radius(local_pts: np.ndarray, k: int, world: int, sample: int = 256, seed: int = 0) -> float:
-    """A rank's slice is a uniform 1/world subsample of the cloud, so its ceil(k/world)+1-th
-    neighbour distance estimates the cloud's k-th.  Brute force on a small sample; the result
-    only sizes the halo (exactness is verified afterwards)."""
-    rng = np.random.default_rng(seed)
-    n = local_pts.shape[0]
-    q = local_pts[rng.integers(0, n, size=min(sample, n)), :3].astype(np.float64)
-    base = local_pts[rng.integers(0, n, size=min(50_000, n)), :3].astype(np.float64)
-    kk = min(len(base) - 1, int(math.ceil(k / world)) + 1)
-    scale = (len(base) / n) ** 0.5  # the base is itself a subsample of the slice (surface: r ~ density^-1/2)
-    d = ((q[:, None, :] - base[None, :, :]) ** 2).sum(-1)
-    kth = np.sqrt(np.partition(d, kk, axis=1)[:, kk])
-    return float(np.quantile(kth, 0.99) * scale * 1.5)
+def as_torch(out: api.ShardOut, device: int) -> dict:
+    """Zero-copy torch views of one shard's result (valid until the comm's next call)."""
+    dev = torch.device("cuda", device)
+    res = {}
+    for name, a in api.Comm.arrays(out).items():
+        if a is None or out.n_owned == 0:
+            res[name] = None
+        else:
+            res[name] = torch.as_tensor(a, device=dev)
+    return res

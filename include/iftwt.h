@@ -244,6 +244,85 @@ IFTWT_API int iftwt_normals_device(iftwt_ctx* ctx, int k, float* d_out4);
  * single-GPU graph / seeds / IFT stages.  The cloud must be set. */
 IFTWT_API int iftwt_set_knn_rows_device(iftwt_ctx* ctx, int k, const int32_t* d_idx, const float* d_d2);
 
+/* ---- Morton-range sharded k-NN / normals across the GPUs of one node (BASELINE config 4) ------
+ * The reference has no multi-device path; what is sharded are its per-point loops — nearestKSearch
+ * (graph.hpp:245) and NormalEstimationOMP::compute (main.cpp:102-109).  Points are partitioned by
+ * contiguous ranges of a coarse Morton key, one range per rank; every rank also receives the halo
+ * (the points of the 26 coarse cells around each of its own) from its peers over NVLink (grouped
+ * ncclSend / ncclRecv), runs the single-GPU kernels, and keeps the rows of the points it owns,
+ * translated to GLOBAL point ids.  The rows are bit-identical to what one GPU computes on the
+ * whole cloud (ties break by global id).  The IFT does not shard: iftwt_sharded_segment gathers
+ * the rows to one rank and runs graph / seeds / IFT there.  (csrc/shard.cu) */
+typedef struct iftwt_comm iftwt_comm;
+
+#define IFTWT_COMM_ID_BYTES 128
+#define IFTWT_COMM_MAX_RANKS 8
+
+/* One process per GPU: rank 0 calls iftwt_comm_unique_id (ncclGetUniqueId) and hands the 128 bytes to
+ * every rank over any side channel; every rank then calls iftwt_comm_create (ncclCommInitRank). */
+IFTWT_API int iftwt_comm_unique_id(void* id128);
+IFTWT_API int iftwt_comm_create(iftwt_comm** out, const void* id128, int nranks, int rank, int device);
+/* One process driving ndev GPUs (ncclCommInitAll); shard i is rank i on devices[i].  Naming the
+ * same device ndev times gives ndev shards that time-share that GPU, with device-to-device copies
+ * as transport (NCCL refuses duplicate devices): the whole path on a single GPU, for testing. */
+IFTWT_API int iftwt_comm_create_all(iftwt_comm** out, int ndev, const int* devices);
+IFTWT_API void iftwt_comm_destroy(iftwt_comm* comm);
+IFTWT_API const char* iftwt_comm_last_error(const iftwt_comm* comm); /* comm may be NULL */
+IFTWT_API int iftwt_comm_info(const iftwt_comm* comm, int* nranks, int* n_local, int* first_local_rank);
+/* The ctx of local shard `local_index` (owned by the comm).  After iftwt_sharded_segment the root's
+ * ctx holds the whole cloud, its graph and the IFT result: iftwt_region_adjacency, iftwt_cluster,
+ * iftwt_graph_csr ... apply to it. */
+IFTWT_API iftwt_ctx* iftwt_comm_ctx(iftwt_comm* comm, int local_index);
+
+/* A rank's slice of the cloud: DEVICE packed float4 {x,y,z,intensity} on the shard's device.  The
+ * slices of ranks 0, 1, ... are consecutive ranges of global point ids (gid0 of rank r+1 =
+ * gid0 + n of rank r, rank 0 starts at 0); at most 2^31 - 1 points in all. */
+typedef struct iftwt_shard_in {
+  const void* d_points;
+  size_t n;
+  uint64_t gid0;
+} iftwt_shard_in;
+
+/* Result of one shard.  Device pointers are owned by the comm and valid until its next call. */
+typedef struct iftwt_shard_out {
+  size_t n_owned;            /* points of the Morton range this rank owns                      */
+  size_t n_halo;             /* halo points received on top of them                            */
+  size_t n_total;            /* points of the whole cloud                                      */
+  int k;
+  int attempts;              /* exchanges run (the halo radius doubles after a violated check) */
+  const uint32_t* d_gid;     /* [n_owned] global ids, ascending                                */
+  const float* d_points;     /* [n_owned] float4                                               */
+  const int32_t* d_knn;      /* [n_owned * k] global ids of the neighbours, canonical (d2, id) order, -1 padded */
+  const float* d_d2;         /* [n_owned * k]                                                  */
+  const float* d_normals;    /* [n_owned] float4 {nx,ny,nz,curvature}, NULL when not requested */
+  double halo_radius;        /* the radius the accepted exchange used                          */
+  double kth_distance_max;   /* largest k-th neighbour distance over the WHOLE cloud: the smallest radius that
+                                passes the check (a caller that segments similar clouds repeatedly passes a
+                                little more than this to its next call)                        */
+  uint64_t halo_bytes_sent;      /* halo copies this rank sent to its peers (points + ids)     */
+  uint64_t exchange_bytes_sent;  /* everything it sent (owner redistribution + halo)           */
+  float ms_estimate;         /* CUDA-event times of the last accepted exchange: halo-radius estimate, */
+  float ms_partition;        /* bbox / histogram / owner table / route / pack,                 */
+  float ms_exchange;         /* the grouped send / recv,                                       */
+  float ms_compute;          /* grid + k-NN + normals on owned + halo points,                  */
+  float ms_export;           /* rows to global ids + exactness check                           */
+  float knn_cell_ms;         /* the k-NN fast-path kernel inside ms_compute                    */
+} iftwt_shard_out;
+
+/* `in` / `out`: one entry per LOCAL shard (1 in the process-per-GPU mode).  halo_radius <= 0: estimated
+ * (the k-th neighbour distance inside a slice bounds the cloud's from above).  Exactness does not
+ * depend on the radius: a row whose k-th distance exceeds it is detected (ncclAllReduce) and the
+ * exchange is redone with twice the radius.  Collective: every rank of the comm must call it. */
+IFTWT_API int iftwt_sharded_knn_normals(iftwt_comm* comm, const iftwt_shard_in* in, int k, int want_normals,
+                                        double halo_radius, iftwt_shard_out* out);
+/* BASELINE config 4 in one call: sharded k-NN + normals, rows / normals / points gathered to rank
+ * `root` (grouped ncclSend / ncclRecv), then graph, region-growing seeds and the IFT on root's GPU.
+ * cost / label (HOST, n_total entries in global id order, may be NULL) and *n_seeds are written by the
+ * process that holds `root` only.  Needs k_normals == k_graph == rg.number_of_neighbours. */
+IFTWT_API int iftwt_sharded_segment(iftwt_comm* comm, const iftwt_shard_in* in, const iftwt_segment_params* params,
+                                    double halo_radius, int root, uint32_t* cost, uint32_t* label, size_t* n_seeds,
+                                    iftwt_shard_out* out);
+
 /* ---- colour path (graco.hpp, main.cpp:16-89): the cloud's 4th channel carries PCL's packed
  * rgb float (pcl::PointXYZRGB: iftwt_set_cloud(points, 32, n, 0, 16)) -------------------- */
 

@@ -1,7 +1,11 @@
-"""Host-side logic of the Morton-range sharded k-NN (iftwt_rg_b200/sharded.py) on CPU:
-world_size 2 and 3, gloo backend, the oracle standing in for the GPU kernels.  The rows every
-rank returns must be the exact global k-NN (ids, order and distances) of the points it owns,
-and the ranks together must own every point exactly once."""
+"""The world_size > 1 logic of the Morton-range sharded k-NN on CPU: world_size 2 and 3, gloo backend.
+
+The product does the partition / halo / exchange in CUDA + NCCL (csrc/shard.cu); what can run
+without a GPU is (a) its reference restatement in plain torch.distributed (oracle/sharded_ref.py),
+the oracle standing in for the GPU kernels — the rows every rank returns must be the exact global
+k-NN (ids, order and distances) of the points it owns, and the ranks together must own every point
+exactly once — and (b) the host side of the product's process-per-GPU mode
+(iftwt_rg_b200/sharded.py: slice bounds, hand-over of the communicator id)."""
 import os
 import socket
 
@@ -11,7 +15,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from iftwt_rg_b200 import sharded, synth
+from iftwt_rg_b200 import synth
+from oracle import sharded_ref as sharded
 
 
 def _free_port():
@@ -83,3 +88,30 @@ def test_partition_is_contiguous_in_morton_order_and_balanced():
     owner = part.owner_of_cells(part.cells(pts[:, :3]))
     counts = torch.bincount(owner, minlength=4)
     assert counts.min() > 0.5 * 50_000 / 4 and counts.max() < 1.6 * 50_000 / 4
+
+
+def _id_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from iftwt_rg_b200 import sharded as host
+        uid = bytes(range(128)) if rank == 0 else None   # stands in for ncclGetUniqueId's 128 bytes
+        got = host.broadcast_id(uid)
+        with open(os.path.join(out_dir, f"id{rank}.bin"), "wb") as f:
+            f.write(got)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_host_side_of_the_product_path(tmp_path):
+    """iftwt_rg_b200/sharded.py: the slices are the contiguous ascending id ranges iftwt_shard_in asks for,
+    and the communicator id reaches every rank intact (world 2, gloo)."""
+    from iftwt_rg_b200 import sharded as host
+    for n, world in ((10, 3), (100_000_001, 8), (5, 8)):
+        b = [host.slice_bounds(n, world, r) for r in range(world)]
+        assert b[0][0] == 0 and b[-1][1] == n
+        assert all(b[r][1] == b[r + 1][0] for r in range(world - 1))
+    mp.spawn(_id_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert open(os.path.join(tmp_path, f"id{r}.bin"), "rb").read() == bytes(range(128))
