@@ -65,6 +65,8 @@ def parse():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS) + ["cfg4"])
     ap.add_argument("--no-sharded", action="store_true",
                     help="N > 1: skip detail.sharded (the cfg4-style Morton-range sharded pass)")
+    ap.add_argument("--sharded-per-gpu", type=int, default=CFG4_PER_GPU,
+                    help="points per GPU of detail.sharded (default: cfg4's share at 8 GPUs)")
     ap.add_argument("--points", type=int, default=0)
     ap.add_argument("--k", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=1_000_000,
@@ -765,8 +767,8 @@ def main():
         wd.daemon = True
         wd.start()
         try:
-            sh = sharded_detail(args, torch, dist, api, world, rank, local, CFG4_PER_GPU * world, CFG4["k"],
-                                max(1, round(CFG4_PER_GPU * world / 10_000_000)), steps=5)
+            sh = sharded_detail(args, torch, dist, api, world, rank, local, args.sharded_per_gpu * world, CFG4["k"],
+                                max(1, round(args.sharded_per_gpu * world / 10_000_000)), steps=5)
         except Exception as e:
             sh = {"error": repr(e)[:400]}
         wd.cancel()

@@ -182,32 +182,31 @@ __device__ __forceinline__ void cell_queries(const CellWarp& w, const float* __r
           ka = min(ka, tc);
           kc = max(kc, ta);
         }
-        CX(16, l16); CX(8, l8); CX(4, l4); CX(2, l2); CX(1, l1);
+        // k <= 32 here (E == 2): only the lower half is ever written, so only ka is sorted on
+        // (five steps on one key instead of two); of the upper half only its minimum matters — it is the
+        // successor of position 31 in the tie check
+#define CX1(mask, lower)                                       \
+  {                                                            \
+    const u32 ta = __shfl_xor_sync(FULL, ka, mask);            \
+    ka = (lower) ? min(ka, ta) : max(ka, ta);                  \
+  }
+        CX1(16, l16); CX1(8, l8); CX1(4, l4); CX1(2, l2); CX1(1, l1);
+#undef CX1
 #undef CX
-        // sorted position lane holds ka, position lane + 32 holds kc; the successor of position 31 is 32
         u32 na = __shfl_down_sync(FULL, ka, 1);
-        const u32 nc = __shfl_down_sync(FULL, kc, 1);
-        const u32 c0 = __shfl_sync(FULL, kc, 0);
+        const u32 c0 = __reduce_min_sync(FULL, kc);
         if (lane == 31) na = c0;
-        const bool tie = ((ka >> 6) == (na >> 6) && na != 0xFFFFFFFFu) ||
-                         (lane < 31 && (kc >> 6) == (nc >> 6) && nc != 0xFFFFFFFFu);
+        const bool tie = (ka >> 6) == (na >> 6) && na != 0xFFFFFFFFu;
         if (!__any_sync(FULL, tie)) {
           ranked = true;
-          u32* nrow = nbr + (size_t)qid * k;
-          float* drow = nd2 + (size_t)qid * k;
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const u32 key = e ? kc : ka;
-            const int p = lane + 32 * e;
-            if (p < k) {  // cnt >= k: the first k positions hold survivors
-              const u32 i = key & 63u;
-              const u32 slot = w.s_slot[i], db = w.s_d2[i];
-              nrow[p] = w.s_id[slot];
-              drow[p] = __uint_as_float(db);
-              if (p == k - 1) {
-                kth[qid] = ((u64)db << 32) | (u64)__float_as_uint(w.s_pts[slot].w);
-                kb = db;
-              }
+          if (lane < k) {  // cnt >= k: the first k positions hold survivors
+            const u32 i = ka & 63u;
+            const u32 slot = w.s_slot[i], db = w.s_d2[i];
+            nbr[(size_t)qid * k + lane] = w.s_id[slot];
+            nd2[(size_t)qid * k + lane] = __uint_as_float(db);
+            if (lane == k - 1) {
+              kth[qid] = ((u64)db << 32) | (u64)__float_as_uint(w.s_pts[slot].w);
+              kb = db;
             }
           }
         }

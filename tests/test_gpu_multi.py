@@ -36,14 +36,67 @@ def _torchrun(n, script, *args, timeout=900):
     return json.loads(lines[-1])
 
 
-def test_sharded_knn_two_gpus_equals_single_gpu():
+def test_sharded_two_gpus_nccl_single_process():
+    """iftwt_comm_create_all over two DIFFERENT devices = ncclCommInitAll: the grouped ncclSend / ncclRecv
+    exchange instead of the device-to-device copies of the single-GPU test mode; rows and the segmentation
+    bit-identical to one GPU."""
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
-    r = _torchrun(2, "tools/sharded_run.py", "--points", "2000000", "--k", "16", "--verify")
-    assert r["verify_rows_equal"] is True
-    assert sum(r["owned_per_rank"]) == 2000000 and min(r["owned_per_rank"]) > 600000
-    assert 0 < sum(r["halo_per_rank"]) < 400000
-    assert r["stats"]["n_seeds"] > 0
+    import numpy as np
+    import torch
+    from iftwt_rg_b200 import api, sharded, synth
+    pts = synth.scene_facade(400_000, seed=0x2A)
+    n, k = len(pts), 16
+    rg = api.RgParams(50, 10000, k, 0.1, 1.0)
+    with api.Context(0) as ctx:
+        ctx.set_cloud(pts)
+        ridx, rd2 = ctx.knn(k)
+        rn = ctx.normals(k)
+        rcost, rlabel, rns = ctx.segment(k, k, rg)
+    bounds = [sharded.slice_bounds(n, 2, r) for r in range(2)]
+    slabs = [torch.from_numpy(np.ascontiguousarray(pts[lo:hi])).to(torch.device("cuda", r))
+             for r, (lo, hi) in enumerate(bounds)]
+    for r in range(2):
+        torch.cuda.synchronize(r)
+    with api.Comm.all([0, 1]) as cm:
+        sl = [(t.data_ptr(), t.shape[0], lo) for t, (lo, hi) in zip(slabs, bounds)]
+        outs = cm.sharded_knn_normals(sl, k, True, 0.0)
+        seen = np.zeros(n, np.int32)
+        for r, o in enumerate(outs):
+            v = {name: t.cpu().numpy() for name, t in sharded.as_torch(o, r).items()}
+            gid = v["gid"]
+            seen[gid] += 1
+            assert np.array_equal(v["knn"], ridx[gid]) and np.array_equal(v["d2"].view(np.uint32), rd2[gid].view(np.uint32))
+            assert np.array_equal(v["normals"].view(np.uint32), rn[gid].view(np.uint32))
+            assert o.halo_bytes_sent > 0 and o.attempts == 1
+        assert np.all(seen == 1)
+        cost, label, ns, _ = cm.sharded_segment(sl, k, rg, root=1, n_total=n)
+        assert ns == rns and np.array_equal(cost, rcost) and np.array_equal(label, rlabel)
+
+
+def test_bench_cfg4_two_gpus():
+    """bench.py --workload cfg4 under torchrun: one process per GPU, ncclCommInitRank, iftwt_sharded_segment."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = _torchrun(2, "bench.py", "--gpus", "2", "--steps", "2", "--warmup", "3", "--workload", "cfg4", "--points",
+                  "4000000")
+    assert r["n_gpus"] == 2 and r["scaling"] == "strong" and r["value"] > 0 and r["gpu_launches"] > 0
+    d = r["detail"]["sharded_knn_normals"]
+    assert d["verify_rows_equal"] is True and d["verified_rows"] > 100000
+    assert sum(d["owned_per_rank"]) == 4000000 and min(d["owned_per_rank"]) > 1200000
+    assert 0 < sum(d["halo_per_rank"]) < 800000 and d["halo_bytes_over_nvlink"] > 0
+    assert r["detail"]["seeds"] > 0 and r["e2e"]["value"] > 0
+
+
+def test_bench_two_gpus_default_line_carries_the_sharded_pass():
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = _torchrun(2, "bench.py", "--gpus", "2", "--steps", "2", "--warmup", "3", "--points", "1000000",
+                  "--sharded-per-gpu", "1500000", "--no-e2e")
+    assert r["n_gpus"] == 2 and r["scaling"] == "weak" and r["value"] > 0 and r["gpu_launches"] > 0
+    sh = r["detail"]["sharded"]
+    assert "error" not in sh, sh
+    assert sh["verify_rows_equal"] is True and sh["knn_normals_ms"] > 0 and sh["segment_seeds"] > 0
 
 
 def test_bench_two_gpus_weak_scaling_line():
