@@ -127,6 +127,15 @@ def load_library(build_if_missing: bool = True):
     lib.iftwt_synchronize.argtypes = [vp]
     lib.iftwt_stream.argtypes = [vp]
     lib.iftwt_stream.restype = vp
+    lib.iftwt_batch_create.argtypes = [C.POINTER(vp), i32, i32]
+    lib.iftwt_batch_destroy.argtypes = [vp]
+    lib.iftwt_batch_destroy.restype = None
+    lib.iftwt_batch_last_error.argtypes = [vp]
+    lib.iftwt_batch_last_error.restype = C.c_char_p
+    lib.iftwt_batch_ctx.argtypes = [vp, i32]
+    lib.iftwt_batch_ctx.restype = vp
+    lib.iftwt_batch_segment.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), sz, i32, C.POINTER(SegmentParams),
+                                        C.POINTER(vp), C.POINTER(vp), C.POINTER(sz)]
     lib.iftwt_comm_unique_id.argtypes = [vp]
     lib.iftwt_comm_create.argtypes = [C.POINTER(vp), vp, i32, i32, i32]
     lib.iftwt_comm_create_all.argtypes = [C.POINTER(vp), i32, C.POINTER(i32)]
@@ -396,6 +405,62 @@ class Context:
         return int(self._lib.iftwt_stream(self._h) or 0)
 
 
+class Batch:
+    """A batch of clouds on one GPU, several lanes (ctx + stream + host thread) pulling from one queue
+    (include/iftwt.h: iftwt_batch_*; BASELINE config 5)."""
+
+    def __init__(self, device: int = 0, lanes: int = 3):
+        self._lib = load_library()
+        h = C.c_void_p()
+        rc = self._lib.iftwt_batch_create(C.byref(h), device, lanes)
+        if rc != 0:
+            raise IftwtError(rc, self._lib.iftwt_batch_last_error(None).decode())
+        self._h = h
+        self.lanes = lanes
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.iftwt_batch_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def ctx(self, lane: int) -> Context:
+        return Context(_borrowed=self._lib.iftwt_batch_ctx(self._h, lane))
+
+    def segment(self, clouds, k: int, rg: RgParams, ns=None, on_device: bool = False, cost=None, label=None,
+                gradient_weights: bool = False):
+        """clouds: host (n_i, 4) float32 arrays, or (device_ptr, n_i) pairs with on_device=True.
+        cost / label: lists of uint32 arrays (or None: results stay on the lanes' devices).  Returns n_seeds."""
+        B = len(clouds)
+        if on_device:
+            ptrs = (C.c_void_p * B)(*[C.c_void_p(int(p)) for p, _ in clouds])
+            sizes = (C.c_size_t * B)(*[int(m) for _, m in clouds])
+        else:
+            for a in clouds:
+                assert a.flags.c_contiguous and a.dtype == np.float32 and a.shape[1] == 4
+            ptrs = (C.c_void_p * B)(*[a.ctypes.data_as(C.c_void_p) for a in clouds])
+            sizes = (C.c_size_t * B)(*[a.shape[0] for a in clouds])
+        cp = (C.c_void_p * B)(*[None if cost is None else cost[i].ctypes.data_as(C.c_void_p) for i in range(B)])
+        lp = (C.c_void_p * B)(*[None if label is None else label[i].ctypes.data_as(C.c_void_p) for i in range(B)])
+        seeds = (C.c_size_t * B)()
+        p = SegmentParams(k, k, rg, 1 if gradient_weights else 0)
+        rc = self._lib.iftwt_batch_segment(self._h, ptrs, sizes, B, 1 if on_device else 0, C.byref(p), cp, lp, seeds)
+        if rc != 0:
+            raise IftwtError(rc, self._lib.iftwt_batch_last_error(self._h).decode())
+        return list(seeds)
+
+
 class DeviceArray:
     """A device buffer owned by the library, seen through __cuda_array_interface__ (zero copy:
     torch.as_tensor(x, device="cuda") / cupy.asarray(x) wrap it without moving data)."""
@@ -493,17 +558,19 @@ class Comm:
         return list(outs)
 
     def sharded_segment(self, slices, k: int, rg: RgParams, root: int = 0, halo_radius: float = 0.0,
-                        n_total: int | None = None, download: bool = True, gradient_weights: bool = False):
+                        n_total: int | None = None, download: bool = True, gradient_weights: bool = False,
+                        cost: np.ndarray | None = None, label: np.ndarray | None = None):
         """BASELINE config 4.  Returns (cost, label, n_seeds, outs); cost / label are None unless this
-        process holds `root`, downloads and knows n_total."""
+        process holds `root`, downloads and knows n_total (or passes its own n_total-entry buffers)."""
         ins = self._ins(slices)
         outs = (ShardOut * self.n_local)()
         p = SegmentParams(k, k, rg, 1 if gradient_weights else 0)
         ns = C.c_size_t(0)
         info = self.info()
         holds_root = info["first_local_rank"] <= root < info["first_local_rank"] + info["n_local"]
-        cost = label = None
-        if download and holds_root and n_total:
+        if not (download and holds_root):
+            cost = label = None
+        elif n_total and cost is None:
             cost = np.empty(n_total, np.uint32)
             label = np.empty(n_total, np.uint32)
         self._check(self._lib.iftwt_sharded_segment(self._h, ins, C.byref(p), float(halo_radius), root, _ptr(cost),

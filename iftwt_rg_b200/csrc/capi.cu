@@ -3,7 +3,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -641,5 +643,111 @@ int iftwt_synchronize(iftwt_ctx* c) {
 }
 
 void* iftwt_stream(iftwt_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+}  // extern "C"
+
+// ---- batch of clouds on one GPU (BASELINE config 5) ------------------------------------------------
+// A 2 M-point cloud does not fill a B200 for long: 162 of its IFT level launches, the label-min sweeps of
+// the seed stage and every host round trip leave most SMs idle.  A batch is therefore run on several
+// LANES — one ctx, one stream and one host thread each, independent by the ABI's contract — that pull
+// clouds from one queue: the latency-bound stretches of one cloud are filled by the kernels of the
+// others.  Results are those of iftwt_segment on each cloud by construction.
+struct iftwt_batch {
+  int device = 0;
+  std::vector<iftwt_ctx*> lanes;
+  std::string err;
+};
+
+extern "C" {
+
+int iftwt_batch_create(iftwt_batch** out, int device, int lanes) {
+  if (!out) {
+    g_err = "null out pointer";
+    return IFTWT_ERR_INVALID;
+  }
+  *out = nullptr;
+  if (lanes < 1 || lanes > 16) {
+    g_err = "lanes must be in [1, 16]";
+    return IFTWT_ERR_INVALID;
+  }
+  iftwt_batch* b = new (std::nothrow) iftwt_batch();
+  if (!b) {
+    g_err = "out of host memory";
+    return IFTWT_ERR_CUDA;
+  }
+  b->device = device;
+  for (int l = 0; l < lanes; ++l) {
+    iftwt_ctx* c = nullptr;
+    int rc = iftwt_create(&c, device);
+    if (rc != IFTWT_OK) {
+      iftwt_batch_destroy(b);
+      return rc;
+    }
+    b->lanes.push_back(c);
+  }
+  *out = b;
+  return IFTWT_OK;
+}
+
+void iftwt_batch_destroy(iftwt_batch* b) {
+  if (!b) return;
+  for (iftwt_ctx* c : b->lanes) iftwt_destroy(c);
+  delete b;
+}
+
+const char* iftwt_batch_last_error(const iftwt_batch* b) { return b ? b->err.c_str() : g_err.c_str(); }
+
+iftwt_ctx* iftwt_batch_ctx(iftwt_batch* b, int lane) {
+  if (!b || lane < 0 || (size_t)lane >= b->lanes.size()) return nullptr;
+  return b->lanes[lane];
+}
+
+int iftwt_batch_segment(iftwt_batch* b, const void* const* clouds, const size_t* n, size_t B, int clouds_on_device,
+                        const iftwt_segment_params* params, uint32_t* const* cost, uint32_t* const* label,
+                        size_t* n_seeds) {
+  if (!b) {
+    g_err = "null batch";
+    return IFTWT_ERR_INVALID;
+  }
+  if (!clouds || !n || !params) {
+    b->err = "null argument";
+    return IFTWT_ERR_INVALID;
+  }
+  std::atomic<size_t> next(0);
+  std::atomic<int> first_rc(IFTWT_OK);
+  std::vector<std::string> errs(b->lanes.size());
+  auto work = [&](size_t lane) {
+    iftwt_ctx* c = b->lanes[lane];
+    while (first_rc.load() == IFTWT_OK) {
+      const size_t i = next.fetch_add(1);
+      if (i >= B) break;
+      int rc = clouds_on_device ? iftwt_set_cloud_device(c, clouds[i], n[i])
+                                : iftwt_set_cloud(c, clouds[i], 16, n[i], 0, 12);
+      size_t ns = 0;
+      if (rc == IFTWT_OK)
+        rc = iftwt_segment(c, params, cost ? cost[i] : nullptr, label ? label[i] : nullptr, &ns);
+      if (rc != IFTWT_OK) {
+        errs[lane] = "cloud " + std::to_string(i) + ": " + c->err;
+        int expected = IFTWT_OK;
+        first_rc.compare_exchange_strong(expected, rc);
+        break;
+      }
+      if (n_seeds) n_seeds[i] = ns;
+    }
+  };
+  std::vector<std::thread> th;
+  for (size_t l = 1; l < b->lanes.size() && l < B; ++l) th.emplace_back(work, l);
+  work(0);
+  for (std::thread& t : th) t.join();
+  if (first_rc.load() != IFTWT_OK) {
+    for (const std::string& e : errs)
+      if (!e.empty()) {
+        b->err = e;
+        break;
+      }
+    return first_rc.load();
+  }
+  return IFTWT_OK;
+}
 
 }  // extern "C"

@@ -12,6 +12,8 @@
 // the three elementary functions of the eigen solver are evaluated by the fixed
 // binary64 series of DESIGN.md ("spec trig") and rounded once to binary32 — every
 // step is a correctly rounded IEEE operation on both machines.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 #define SID_NONE 0xFFFFFFFFu
@@ -196,47 +198,48 @@ __device__ __forceinline__ float4 finish_normal(float a0, float a1, float a2, fl
 // The one-thread-per-point form of this kernel (rows read at a 4k-byte stride, every gather on
 // its own line) ran at 97 % L1 tag throughput: 64 requests x 32 lines per warp
 // (profiles/r01_misc_kernels_ncu.txt).
-#define NRM_C 16
-#define NRM_B 8  // gather rounds in flight per lane
-#define NRM_STRIDE (NRM_C * 3 + 1)
-#define NRM_WARPS 4
-__global__ void __launch_bounds__(NRM_WARPS * 32)
+// Tile shape: C neighbours at a time, B gather rounds in flight per lane, W warps per block.
+// (C, B, W) = (16, 8, 4) was round 1's; the variants are selectable with IFTWT_NRM_VARIANT for the
+// tuning sweep (tools/tune.py), the default is the fastest measured on cfg3.
+template <int C, int B, int W>
+__global__ void __launch_bounds__(W * 32)
 normals_kernel(const float4* __restrict__ spts, const u32* __restrict__ nbr, u32 n, int k,
                float4* __restrict__ out) {
-  __shared__ float s_nb[NRM_WARPS][32 * NRM_STRIDE];
+  constexpr int STRIDE = C * 3 + 1;
+  __shared__ float s_nb[W][32 * STRIDE];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const u32 u0 = (blockIdx.x * NRM_WARPS + warp) * 32u;
+  const u32 u0 = (blockIdx.x * W + warp) * 32u;
   if (u0 >= n) return;
   float* nb = s_nb[warp];
   const u32 i = u0 + lane;
   int cnt = 0;
   float a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0, a8 = 0;
   const float nanv = __int_as_float(0x7FC00000);
-  for (int c0 = 0; c0 < k; c0 += NRM_C) {
-    const int cc = min(NRM_C, k - c0);
-    for (int e0 = lane; e0 < 32 * NRM_C; e0 += 32 * NRM_B) {
-      u32 v[NRM_B];
-      float4 P[NRM_B];
+  for (int c0 = 0; c0 < k; c0 += C) {
+    const int cc = min(C, k - c0);
+    for (int e0 = lane; e0 < 32 * C; e0 += 32 * B) {
+      u32 v[B];
+      float4 P[B];
 #pragma unroll
-      for (int b = 0; b < NRM_B; ++b) {
-        const int e = e0 + 32 * b, p = e / NRM_C, j = e % NRM_C;
+      for (int b = 0; b < B; ++b) {
+        const int e = e0 + 32 * b, p = e / C, j = e % C;
         v[b] = (j < cc && u0 + p < n) ? nbr[(size_t)(u0 + p) * k + c0 + j] : SID_NONE;
       }
 #pragma unroll
-      for (int b = 0; b < NRM_B; ++b) P[b] = v[b] != SID_NONE ? spts[v[b]] : make_float4(nanv, 0.f, 0.f, 0.f);
+      for (int b = 0; b < B; ++b) P[b] = v[b] != SID_NONE ? spts[v[b]] : make_float4(nanv, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int b = 0; b < NRM_B; ++b) {
-        const int e = e0 + 32 * b, p = e / NRM_C, j = e % NRM_C;
-        float* d = nb + p * NRM_STRIDE + 3 * j;
+      for (int b = 0; b < B; ++b) {
+        const int e = e0 + 32 * b, p = e / C, j = e % C;
+        float* d = nb + p * STRIDE + 3 * j;
         d[0] = P[b].x;
         d[1] = P[b].y;
         d[2] = P[b].z;
       }
     }
     __syncwarp();
-    const float* mine = nb + lane * NRM_STRIDE;
+    const float* mine = nb + lane * STRIDE;
 #pragma unroll 4
-    for (int j = 0; j < NRM_C; ++j) {
+    for (int j = 0; j < C; ++j) {
       const float px = mine[3 * j], py = mine[3 * j + 1], pz = mine[3 * j + 2];
       if (px != px) continue;  // missing neighbour (or past the row's end)
       a0 += px * px;
@@ -263,8 +266,20 @@ int normals_run(iftwt_ctx* c) {
   StageTimer st(c, IFTWT_STAGE_NORMALS);
   const u32 n = (u32)c->n;
   ENSURE(c, c->nrm, (size_t)n * 16);
-  LAUNCH(c, normals_kernel, div_up(n, NRM_WARPS * 32), NRM_WARPS * 32, 0, c->spts.as<float4>(), c->nbr.as<u32>(), n, c->knn_k,
-         c->nrm.as<float4>());
+  const int variant = getenv("IFTWT_NRM_VARIANT") ? atoi(getenv("IFTWT_NRM_VARIANT")) : 0;
+#define NRM_LAUNCH(C, B, W)                                                                                       \
+  LAUNCH(c, (normals_kernel<C, B, W>), div_up(n, W * 32), W * 32, 0, c->spts.as<float4>(), c->nbr.as<u32>(), n, \
+         c->knn_k, c->nrm.as<float4>())
+  switch (variant) {
+    case 1: NRM_LAUNCH(16, 4, 4); break;
+    case 2: NRM_LAUNCH(8, 8, 4); break;
+    case 3: NRM_LAUNCH(8, 4, 8); break;
+    case 4: NRM_LAUNCH(8, 8, 8); break;
+    case 5: NRM_LAUNCH(8, 4, 4); break;
+    case 6: NRM_LAUNCH(16, 8, 2); break;
+    default: NRM_LAUNCH(16, 8, 4); break;
+  }
+#undef NRM_LAUNCH
   CHECK_LAUNCH(c);
   c->nrm_k = c->knn_k;
   c->seeds_valid = false;

@@ -23,6 +23,7 @@
 //   5. the snap of every centroid to its nearest input point (k-NN general path).
 #include <cub/cub.cuh>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -77,14 +78,15 @@ __device__ __forceinline__ u64 rg_key(const float4* __restrict__ nrm, const floa
 // long-scoreboard stall cycles per issue: 3.9 ms at 10 M points, k = 32
 // (profiles/r01_top_kernels_ncu_full.txt).
 #define RGA_WARPS 8
-#define RGA_B 4
 __host__ __device__ inline int rga_flag_stride(int k) {  // bytes per vertex, (bytes / 4) odd
   int w = (k + 3) / 4;
   return 4 * (w | 1);
 }
 static size_t rga_smem_bytes(int k) { return (size_t)RGA_WARPS * (32 * 16 + 32 * 8 + 32 * rga_flag_stride(k)); }
-template <bool FUSED>
-__global__ void __launch_bounds__(RGA_WARPS * 32, 4)
+// RGA_B = rounds of loads in flight per lane, MINB = blocks per SM the register allocation must allow
+// ((4, 4) was round 1's: 63 registers, 47 % occupancy; variants selectable with IFTWT_RGA_VARIANT)
+template <bool FUSED, int RGA_B, int MINB>
+__global__ void __launch_bounds__(RGA_WARPS * 32, MINB)
 rg_classify_kernel(const u32* __restrict__ nbr, const float* __restrict__ nd2, const u64* __restrict__ kth,
                    const float4* __restrict__ spts, u64* __restrict__ ow_mask, const float4* __restrict__ nrm, u32 n,
                    int k, float cos_thr, u64* __restrict__ hook_mask, u64* __restrict__ list_mask,
@@ -474,11 +476,25 @@ int fused_graph_rg_run(iftwt_ctx* c, const iftwt_rg_params* p) {
   ENSURE(c, c->rg_masks, (size_t)n * 16);
   u64* hook_mask = c->rg_masks.as<u64>();
   u64* list_mask = hook_mask + n;
-  CU_TRY(c, cudaFuncSetAttribute(rg_classify_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)rga_smem_bytes(k)));
-  LAUNCH(c, rg_classify_kernel<true>, div_up(n, RGA_WARPS * 32), RGA_WARPS * 32, rga_smem_bytes(k), c->nbr.as<u32>(),
-         c->nd2.as<float>(), c->kth.as<u64>(), c->spts.as<float4>(), c->ow_mask.as<u64>(), c->nrm.as<float4>(), n, k,
-         cos_thr, hook_mask, list_mask, c->g_deg.as<u32>(), d_nfwd, c->rg_parent.as<u32>());
+  const int variant = getenv("IFTWT_RGA_VARIANT") ? atoi(getenv("IFTWT_RGA_VARIANT")) : 0;
+#define RGA_LAUNCH(B, MINB)                                                                                          \
+  {                                                                                                                  \
+    CU_TRY(c, cudaFuncSetAttribute(rg_classify_kernel<true, B, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                   (int)rga_smem_bytes(k)));                                                         \
+    LAUNCH(c, (rg_classify_kernel<true, B, MINB>), div_up(n, RGA_WARPS * 32), RGA_WARPS * 32, rga_smem_bytes(k),     \
+           c->nbr.as<u32>(), c->nd2.as<float>(), c->kth.as<u64>(), c->spts.as<float4>(), c->ow_mask.as<u64>(),       \
+           c->nrm.as<float4>(), n, k, cos_thr, hook_mask, list_mask, c->g_deg.as<u32>(), d_nfwd,                     \
+           c->rg_parent.as<u32>());                                                                                  \
+  }
+  switch (variant) {
+    case 1: RGA_LAUNCH(4, 5); break;
+    case 2: RGA_LAUNCH(4, 6); break;
+    case 3: RGA_LAUNCH(2, 6); break;
+    case 4: RGA_LAUNCH(2, 8); break;
+    case 5: RGA_LAUNCH(8, 4); break;
+    default: RGA_LAUNCH(4, 4); break;
+  }
+#undef RGA_LAUNCH
   LAUNCH(c, rg_hook_kernel, div_up(n, 256), 256, 0, c->nbr.as<u32>(), hook_mask, list_mask, n, k,
          c->rg_parent.as<u32>(), d_cnt, arc_u, arc_u + (ne + 1));
   CHECK_LAUNCH(c);
@@ -544,9 +560,9 @@ int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p) {
     ENSURE(c, c->rg_masks, (size_t)n * 16);
     u64* hook_mask = c->rg_masks.as<u64>();
     u64* list_mask = hook_mask + n;
-    CU_TRY(c, cudaFuncSetAttribute(rg_classify_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CU_TRY(c, cudaFuncSetAttribute(rg_classify_kernel<false, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)rga_smem_bytes(k)));
-    LAUNCH(c, rg_classify_kernel<false>, div_up(n, RGA_WARPS * 32), RGA_WARPS * 32, rga_smem_bytes(k),
+    LAUNCH(c, (rg_classify_kernel<false, 4, 4>), div_up(n, RGA_WARPS * 32), RGA_WARPS * 32, rga_smem_bytes(k),
            c->nbr.as<u32>(), (const float*)nullptr, (const u64*)nullptr, (const float4*)nullptr, c->ow_mask.as<u64>(),
            nrm, n, k, cos_thr, hook_mask, list_mask, (u32*)nullptr, (unsigned long long*)nullptr, parent);
     LAUNCH(c, rg_hook_kernel, div_up(n, 256), 256, 0, c->nbr.as<u32>(), hook_mask, list_mask, n, k, parent, d_cnt,

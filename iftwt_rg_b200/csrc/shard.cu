@@ -279,20 +279,16 @@ __global__ void __launch_bounds__(256)
 shard_route_kernel(const float4* __restrict__ pts, u32 n, CoarseGrid g,
                    const unsigned char* __restrict__ owner_of_bin, int W, u32* __restrict__ route,
                    u32* __restrict__ blk_cnt, u32 nblk, u32* __restrict__ owned_cnt) {
-  __shared__ u32 s_cnt[SHARD_MAX_RANKS][8];
-  __shared__ u32 s_own[SHARD_MAX_RANKS];
+  __shared__ u32 s_cnt[SHARD_MAX_RANKS][8];  // per warp: sent to d (low half) | of which owned by d (high half)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x < SHARD_MAX_RANKS) s_own[threadIdx.x] = 0;
-  __syncthreads();
   const u32 i0 = blockIdx.x * PACK_TILE + threadIdx.x * PACK_PPT;
   u32 r[PACK_PPT];
 #pragma unroll
   for (int q = 0; q < PACK_PPT; ++q) {
-    r[q] = 0;
+    r[q] = 0xFFFF0000u;  // no point: no destination, an owner nobody is
     if (i0 + q < n) {
       r[q] = route_of(g, owner_of_bin, pts[i0 + q]);
       route[i0 + q] = r[q];
-      atomicAdd(&s_own[r[q] >> 16], 1u);
     }
   }
 #pragma unroll
@@ -300,8 +296,8 @@ shard_route_kernel(const float4* __restrict__ pts, u32 n, CoarseGrid g,
     if (d >= W) break;
     u32 c = 0;
 #pragma unroll
-    for (int q = 0; q < PACK_PPT; ++q) c += (r[q] >> d) & 1u;
-    c = __reduce_add_sync(0xffffffffu, c);
+    for (int q = 0; q < PACK_PPT; ++q) c += ((r[q] >> d) & 1u) + ((r[q] >> 16) == (u32)d ? 0x10000u : 0u);
+    c = __reduce_add_sync(0xffffffffu, c);   // <= 128 per half: no carry between the halves
     if (lane == 0) s_cnt[d][warp] = c;
   }
   __syncthreads();
@@ -309,8 +305,8 @@ shard_route_kernel(const float4* __restrict__ pts, u32 n, CoarseGrid g,
     u32 t = 0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) t += s_cnt[threadIdx.x][w];
-    blk_cnt[(size_t)threadIdx.x * nblk + blockIdx.x] = t;
-    if (s_own[threadIdx.x]) atomicAdd(&owned_cnt[threadIdx.x], s_own[threadIdx.x]);
+    blk_cnt[(size_t)threadIdx.x * nblk + blockIdx.x] = t & 0xFFFFu;
+    if (t >> 16) atomicAdd(&owned_cnt[threadIdx.x], t >> 16);
   }
 }
 // pass 2: every point is written once per destination, at a position that preserves the input order
@@ -405,19 +401,25 @@ __global__ void shard_export_points_kernel(const u32* __restrict__ owned_idx, u3
     if (kb > viol[1]) atomicMax(viol + 1, kb);
   }
 }
+// global id of every point in the ctx's sorted (Morton) space: the row export then needs ONE gather per
+// entry, and a Morton-local one (gid[perm[sid]] was two, the second at random: 3.1 ms for 12.5 M rows)
+__global__ void shard_gid_sorted_kernel(const u32* __restrict__ gid, const u32* __restrict__ perm, u32 m,
+                                        u32* __restrict__ gid_sorted) {
+  const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < m) gid_sorted[s] = gid[perm[s]] & GID_MASK;
+}
 // per row entry: neighbour translated to its global id
 __global__ void shard_export_rows_kernel(const u32* __restrict__ owned_idx, u32 n_owned, int k,
-                                         const u32* __restrict__ gid, const u32* __restrict__ inv,
-                                         const u32* __restrict__ perm, const u32* __restrict__ nbr,
-                                         const float* __restrict__ nd2, int* __restrict__ o_knn,
-                                         float* __restrict__ o_d2) {
+                                         const u32* __restrict__ gid_sorted, const u32* __restrict__ inv,
+                                         const u32* __restrict__ nbr, const float* __restrict__ nd2,
+                                         int* __restrict__ o_knn, float* __restrict__ o_d2) {
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (size_t)n_owned * k) return;
   const u32 j = (u32)(e / (u32)k);
   const int col = (int)(e - (size_t)j * k);
   const size_t src = (size_t)inv[owned_idx[j]] * k + col;
   const u32 sid = nbr[src];
-  o_knn[e] = sid == SID_NONE ? -1 : (int)(gid[perm[sid]] & GID_MASK);
+  o_knn[e] = sid == SID_NONE ? -1 : (int)gid_sorted[sid];
   o_d2[e] = nd2[src];
 }
 
@@ -736,7 +738,10 @@ static int sharded_knn_normals_impl(iftwt_comm* cm, const iftwt_shard_in* in, in
   double ext = fmax(fmax(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
   if (!(ext > 0.0)) ext = 1.0;
   double s_rad = halo_radius;
-  if (estimate) s_rad = kth2 > 0.f ? 1.25 * sqrt((double)kth2) : ext;  // no estimate (tiny slices): everything everywhere
+  // The sample bounds the k-th distance of the SAMPLED points only; the cloud's largest one (a point on a
+  // sparse rim) was 1.36 x the sample's on the facade.  A wider halo costs little (0.2 % more points at
+  // 12.5 M points per GPU), a violated check costs a whole second exchange: twice the sample's maximum.
+  if (estimate) s_rad = kth2 > 0.f ? 2.0 * sqrt((double)kth2) : ext;  // no estimate (tiny slices): everything everywhere
   for (size_t l = 0; l < L; ++l) cudaEventRecord(cm->sh[l].ev[1], cm->sh[l].ctx->stream);
 
   int attempts = 0;
@@ -904,10 +909,12 @@ static int sharded_knn_normals_impl(iftwt_comm* cm, const iftwt_shard_in* in, in
                   (const float4*)(want_normals ? c->nrm.as<float4>() : nullptr), (const u64*)c->kth.as<u64>(),
                   s2_limit, have_all, s.o_gid.as<u32>(), s.o_pts.as<float4>(),
                   want_normals ? s.o_nrm.as<float4>() : (float4*)nullptr, s.small.as<u32>());
+        u32* gid_sorted = s.flag.as<u32>();  // the flags are consumed: their buffer is reused
+        SH_LAUNCH(s, shard_gid_sorted_kernel, div_up(m, 256), 256, (const u32*)s.recv_gid.as<u32>(),
+                  (const u32*)c->perm.as<u32>(), (u32)m, gid_sorted);
         SH_LAUNCH(s, shard_export_rows_kernel, div_up(no * k, 256), 256, (const u32*)s.owned_idx.as<u32>(), (u32)no, k,
-                  (const u32*)s.recv_gid.as<u32>(), (const u32*)c->inv.as<u32>(), (const u32*)c->perm.as<u32>(),
-                  (const u32*)c->nbr.as<u32>(), (const float*)c->nd2.as<float>(), s.o_knn.as<int>(),
-                  s.o_d2.as<float>());
+                  (const u32*)gid_sorted, (const u32*)c->inv.as<u32>(), (const u32*)c->nbr.as<u32>(),
+                  (const float*)c->nd2.as<float>(), s.o_knn.as<int>(), s.o_d2.as<float>());
       }
       CM_CU(cm, cudaGetLastError());
       cudaEventRecord(s.ev[5], c->stream);

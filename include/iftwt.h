@@ -244,6 +244,23 @@ IFTWT_API int iftwt_normals_device(iftwt_ctx* ctx, int k, float* d_out4);
  * single-GPU graph / seeds / IFT stages.  The cloud must be set. */
 IFTWT_API int iftwt_set_knn_rows_device(iftwt_ctx* ctx, int k, const int32_t* d_idx, const float* d_d2);
 
+/* ---- a batch of clouds on one GPU (BASELINE config 5) ----------------------------------------
+ * The reference segments one cloud per process run (main.cpp:78-148).  A batch object owns `lanes`
+ * ctxs on one device — one stream and one host thread each — that pull clouds from one queue, so the
+ * latency-bound stretches of one cloud (small IFT levels, seed sweeps, host round trips) are filled by
+ * the kernels of the others.  Results are exactly those of iftwt_segment on each cloud. */
+typedef struct iftwt_batch iftwt_batch;
+IFTWT_API int iftwt_batch_create(iftwt_batch** out, int device, int lanes);
+IFTWT_API void iftwt_batch_destroy(iftwt_batch* batch);
+IFTWT_API const char* iftwt_batch_last_error(const iftwt_batch* batch); /* batch may be NULL */
+IFTWT_API iftwt_ctx* iftwt_batch_ctx(iftwt_batch* batch, int lane);     /* e.g. for iftwt_get_stats */
+/* clouds[i]: n[i] packed float4 {x,y,z,intensity} records — DEVICE pointers when clouds_on_device != 0,
+ * host pointers otherwise.  cost / label: B host pointers (each n[i] entries) or NULL; entries may be NULL.
+ * n_seeds: B entries or NULL.  Returns the first error of any cloud. */
+IFTWT_API int iftwt_batch_segment(iftwt_batch* batch, const void* const* clouds, const size_t* n, size_t B,
+                                  int clouds_on_device, const iftwt_segment_params* params, uint32_t* const* cost,
+                                  uint32_t* const* label, size_t* n_seeds);
+
 /* ---- Morton-range sharded k-NN / normals across the GPUs of one node (BASELINE config 4) ------
  * The reference has no multi-device path; what is sharded are its per-point loops — nearestKSearch
  * (graph.hpp:245) and NormalEstimationOMP::compute (main.cpp:102-109).  Points are partitioned by

@@ -30,7 +30,11 @@ def _torchrun(n, script, *args, timeout=900):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
            "--master-addr", "127.0.0.1", "--master-port", str(_port()), script, *args]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
-    assert out.returncode == 0, out.stderr[-3000:]
+    if out.returncode != 0:   # keep the whole story for the post-mortem (gpurun brings gpurun_out/ back)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "torchrun_failure.log"), "a") as f:
+            f.write(" ".join(cmd) + "\n" + out.stdout + "\n" + out.stderr + "\n")
+    assert out.returncode == 0, out.stderr[:1500] + "\n...\n" + out.stderr[-1500:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert lines, out.stdout[-2000:]
     return json.loads(lines[-1])
