@@ -63,8 +63,12 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS) + ["cfg4"])
+    ap.add_argument("--serial-headline", action="store_true",
+                    help="report the one-ctx figure as `value` (default: the iftwt_batch_segment figure)")
     ap.add_argument("--lanes", type=int, default=0,
                     help="lanes of the iftwt_batch measurement (0: 3 for cfg5, 2 otherwise)")
+    ap.add_argument("--no-cfg5", action="store_true",
+                    help="skip detail.cfg5 (BASELINE config 5's batch of 64 2M-point clouds split over the ranks)")
     ap.add_argument("--no-sharded", action="store_true",
                     help="N > 1: skip detail.sharded (the cfg4-style Morton-range sharded pass)")
     ap.add_argument("--sharded-per-gpu", type=int, default=CFG4_PER_GPU,
@@ -223,6 +227,40 @@ class ClockSampler:
         except OSError:
             pass
         return out
+
+
+def place_rank(local: int, world: int) -> dict:
+    """Host placement of a rank before it allocates pinned memory: the cores NVML reports as close to its
+    GPU, split evenly between the ranks that share them, so that the e2e copy threads of eight ranks do not
+    migrate over one another (first-touch then places the pinned buffers on that node).  On a box whose GPUs
+    all report the same CPU set (the B200 pool: one NUMA node, `nvidia-smi topo -m`) only the split applies."""
+    info = {"cpus_before": len(os.sched_getaffinity(0))}
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+        near = allowed
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            ideal = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+            if ideal & set(allowed):
+                near = sorted(ideal & set(allowed))
+            info["gpu_cpu_affinity"] = f"{min(ideal)}-{max(ideal)}" if ideal else None
+        except Exception:
+            pass
+        if world > 1 and len(near) // world >= 3:
+            per = len(near) // world
+            mine = near[local * per:(local + 1) * per]
+            os.sched_setaffinity(0, mine)
+            info["pinned_to"] = f"{mine[0]}-{mine[-1]}"
+        elif near != allowed:
+            os.sched_setaffinity(0, near)
+            info["pinned_to"] = f"{near[0]}-{near[-1]}"
+    except Exception as e:
+        info["error"] = repr(e)[:100]
+    info["cpus_after"] = len(os.sched_getaffinity(0))
+    return info
 
 
 class ShardedRun:
@@ -550,6 +588,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    placement = place_rank(local, world)
 
     def barrier():
         if world > 1:
@@ -618,7 +657,6 @@ def main():
 
     ms_total = timed(step_resident_acc, args.steps)
     stats = ctx.stats()
-    clocks = sampler.stop() if rank == 0 else {}
     launches = int(stats["kernel_launches"])
     value = world * n * args.steps / (ms_total * 1e-3)
 
@@ -628,10 +666,13 @@ def main():
     batch_info = None
     try:
         with api.Batch(local, lanes) as bt:
-            nb = max(args.steps, 2 * lanes)
-            clouds = [(dev_ins[i % per_rank].data_ptr(), n) for i in range(nb)]
-            bt.segment(clouds[: 2 * lanes], k, rg, on_device=True)   # warm-up: allocations of every lane
-            bt.segment(clouds[: 2 * lanes], k, rg, on_device=True)
+            nb = args.steps                                           # EXACTLY K steps = K clouds
+            clouds = [(dev_ins[i % per_rank].data_ptr(), n) for i in range(max(nb, 2 * lanes))]
+            for _ in range(max(2, (max(args.warmup, 3) + 2 * lanes - 1) // (2 * lanes))):
+                bt.segment(clouds[: 2 * lanes], k, rg, on_device=True)   # warm-up: >= W clouds, every lane allocates
+            clouds = clouds[:nb]
+            for l in range(lanes):
+                bt.ctx(l).reset_counters()
             st0 = torch.cuda.ExternalStream(bt.ctx(0).stream(), device=torch.device("cuda", local))
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
@@ -645,11 +686,13 @@ def main():
                 dist.all_reduce(msb, op=dist.ReduceOp.MAX)
             msb = float(msb.item())
             lane_launches = sum(int(bt.ctx(l).stats()["kernel_launches"]) for l in range(lanes))
-            batch_info = {"lanes": lanes, "clouds": nb, "ms_per_cloud": msb / nb,
+            batch_info = {"lanes": lanes, "clouds": nb, "ms_per_cloud": msb / nb, "ms_total": msb,
                           "value": world * n * nb / (msb * 1e-3), "seeds_first_cloud": int(seeds_b[0]),
+                          "gpu_launches": lane_launches,
                           "what": "iftwt_batch_segment, clouds resident in HBM, results left on the device"}
     except Exception as e:
         batch_info = {"error": repr(e)[:300]}
+    clocks = sampler.stop() if rank == 0 else {}
 
     e2e = None
     if not args.no_e2e:
@@ -782,21 +825,63 @@ def main():
                 except Exception as e:  # reported, never fatal: the timed numbers above stand on their own
                     extra["parity"] = {"error": repr(e)[:300]}
         head_value, head_ms, head_launches = value, ms_total / args.steps, launches
-        if args.workload == "cfg5" and batch_info and "value" in batch_info:
-            # config 5's entry point IS the batch call; the one-ctx figure stays in detail.serial_one_ctx
-            head_value, head_ms = batch_info["value"], batch_info["ms_per_cloud"]
+        entry = "iftwt_segment, one ctx, one cloud at a time"
+        if batch_info and "value" in batch_info and not args.serial_headline:
+            # whole-job throughput: the K clouds of the timed region go through iftwt_batch_segment (`lanes` ctxs,
+            # one stream + one host thread each, pulling from one queue).  Every cloud runs the whole pipeline;
+            # the one-ctx figure, which the roofline and the stage times refer to, stays in detail.serial_one_ctx
+            head_value, head_ms, head_launches = batch_info["value"], batch_info["ms_per_cloud"], batch_info["gpu_launches"]
+            entry = f"iftwt_batch_segment, {lanes} lanes on the GPU"
         line = {
             "metric": METRIC, "value": head_value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": head_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
             "config": {"workload": desc if (n == n_default and k == k_default) else f"{gen} n={n} k={k}",
-                       "k": k, "points_per_gpu": n, "parallelism": f"one cloud per GPU x{world}, no collective", "clouds_per_rank": per_rank,
+                       "k": k, "points_per_gpu": n, "entry_point": entry,
+                       "parallelism": f"independent clouds, {world} GPU(s), no data-path collective", "clouds_per_rank": per_rank,
+                       "host_placement": placement,
                        "l2": "inputs (16 B/pt) and every intermediate exceed the 126 MB L2; cloud re-uploaded "
                              "device-to-device each step"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": head_launches, "roofline": roofline,
             "cpu_baseline": cpu, "detail": extra,
         }
     ctx.close()
+    if not args.no_cfg5 and args.workload == "cfg3":
+        # BASELINE config 5 on the same GPUs: 64 clouds of 2 M points, 64 // N per rank through iftwt_batch_segment
+        # (3 lanes), no data-path collective.  At most 8 distinct clouds per rank are generated; the batch cycles.
+        c5 = None
+        try:
+            n5, k5 = 2_000_000, 16
+            mine = max(1, CFG5_BATCH // world)
+            distinct = min(8, mine)
+            dev5 = [torch.from_numpy(synth.scene_primitives(n5, seed=0x1F50 + rank * mine + i)).cuda()
+                    for i in range(distinct)]
+            rg5 = api.RgParams(RG_MIN, RG_MAX, k5, THETA, 1.0)
+            with api.Batch(local, 3) as bt:
+                clouds = [(dev5[i % distinct].data_ptr(), n5) for i in range(mine)]
+                bt.segment(clouds[:6], k5, rg5, on_device=True)
+                bt.segment(clouds[:6], k5, rg5, on_device=True)
+                st0 = torch.cuda.ExternalStream(bt.ctx(0).stream(), device=torch.device("cuda", local))
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                barrier()
+                e0.record(st0)
+                seeds5 = bt.segment(clouds, k5, rg5, on_device=True)
+                e1.record(st0)
+                barrier()
+                ms5 = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+                if world > 1:
+                    dist.all_reduce(ms5, op=dist.ReduceOp.MAX)
+                ms5 = float(ms5.item())
+            c5 = {"workload": WORKLOADS["cfg5"][3], "clouds": mine * world, "clouds_per_gpu": mine,
+                  "distinct_clouds_per_gpu": distinct, "points_per_cloud": n5, "k": k5, "lanes": 3, "batch_ms": ms5,
+                  "clouds_per_s": mine * world / (ms5 * 1e-3), "points_per_s": mine * world * n5 / (ms5 * 1e-3),
+                  "points_per_s_per_gpu": mine * n5 / (ms5 * 1e-3), "seeds_first_cloud": int(seeds5[0]),
+                  "what": "iftwt_batch_segment per rank, clouds resident in HBM, results left on the device"}
+            del dev5
+        except Exception as e:
+            c5 = {"error": repr(e)[:300]}
+        if rank == 0:
+            line["detail"]["cfg5"] = c5
     if world > 1 and not args.no_sharded and args.workload == "cfg3":
         # BASELINE config 4's shape on the same GPUs: k-NN + normals sharded by Morton range with an NCCL halo
         # exchange, inside the library.  A collective that hangs must not cost the line above: a watchdog on
@@ -865,9 +950,12 @@ def main_cfg4(args):
     e2e = None
     if not args.no_e2e:
         # slices from pinned host memory every step, cost + label of the whole cloud back to the host on rank 0
+        # (the copy runs on torch's own stream and is waited for before the library is called: torch must never
+        # see the library's stream as a user of its pinned blocks — it would record an event on that stream when
+        # the block is freed, after iftwt_comm_destroy has destroyed it)
         def step_e2e():
-            with torch.cuda.stream(run.stream):
-                run.dev_pts.copy_(run.host_pts, non_blocking=True)
+            run.dev_pts.copy_(run.host_pts, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
             return run.segment(download=True)
         step_e2e()
         ms_e2e, _ = run.timed(step_e2e, args.steps)

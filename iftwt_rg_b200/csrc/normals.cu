@@ -270,14 +270,16 @@ int normals_run(iftwt_ctx* c) {
 #define NRM_LAUNCH(C, B, W)                                                                                       \
   LAUNCH(c, (normals_kernel<C, B, W>), div_up(n, W * 32), W * 32, 0, c->spts.as<float4>(), c->nbr.as<u32>(), n, \
          c->knn_k, c->nrm.as<float4>())
+  // cfg3 on B200 (tools/tune.py, gpurun_out/r2_tune1.jsonl): (16,8,4) 1.146 ms, (16,4,4) 1.125, (8,8,4) 1.100,
+  // (8,4,8) 1.208, (8,8,8) 1.078, (8,4,4) 1.218, (16,8,2) 1.400
   switch (variant) {
     case 1: NRM_LAUNCH(16, 4, 4); break;
     case 2: NRM_LAUNCH(8, 8, 4); break;
     case 3: NRM_LAUNCH(8, 4, 8); break;
-    case 4: NRM_LAUNCH(8, 8, 8); break;
+    case 4: NRM_LAUNCH(16, 8, 4); break;
     case 5: NRM_LAUNCH(8, 4, 4); break;
     case 6: NRM_LAUNCH(16, 8, 2); break;
-    default: NRM_LAUNCH(16, 8, 4); break;
+    default: NRM_LAUNCH(8, 8, 8); break;
   }
 #undef NRM_LAUNCH
   CHECK_LAUNCH(c);

@@ -214,17 +214,28 @@ IFTWT_API int iftwt_set_intensity(iftwt_ctx* ctx, const float* values);
 IFTWT_API int iftwt_regmin_seeds(iftwt_ctx* ctx, int32_t* seeds, size_t capacity, size_t* n_seeds);
 
 /* ---- region hierarchy (ift.hpp:5-23, 207-243; cluster.hpp:23-229) ---------------------
- * The reference's region bookkeeping and Cluster depend on the sequential conquest order
- * and on container address order; the product definition is the
- * watershed region-adjacency graph with saddle heights and a single-linkage merge along
- * its minimum spanning forest.  All three calls need a finished iftwt_ift / iftwt_segment. */
+ * NOT a reproduction of the reference's getMST() / r_info, and not claimed as one.  The reference
+ * updates r_info inside the relaxation branch of its heap loop (ift.hpp:207-209: once per cost
+ * improvement, not once per vertex), records an edge at a region's FIRST contact with another
+ * (guarded by `status`, ift.hpp:220-222) with the volumes the two regions happen to have at that
+ * moment, and merges their bookkeeping on the spot (ift.hpp:226-240).  Every one of those values is a
+ * function of the sequential relaxation order — which itself depends on container address order
+ * (globals.hpp:37-38) — so no order-free computation reproduces them; Cluster (cluster.hpp) consumes
+ * that map and has undefined behaviour of its own (cluster.hpp:164, 187).  The literal procedure is
+ * restated in the oracle and checked bit for bit against the reference's own code
+ * (tests/test_ref_ift.py); it is test infrastructure.  What the product provides instead
+ *  is the classical, order-free watershed hierarchy on the same IFT result: the region
+ * adjacency graph with saddle heights, per-region area and height, and a single-linkage merge along
+ * its minimum spanning forest down to num_regions.  All three calls need a finished iftwt_ift /
+ * iftwt_segment. */
 
 /* Region adjacency: pairs a < b of seed ids whose regions touch, saddle = min over the
- * touching arcs of max(cost[u], cost[v]).  Sorted by (a, b).  Replaces getMST (ift.hpp:45-47). */
+ * touching arcs of max(cost[u], cost[v]).  Sorted by (a, b).  The product's stand-in for the edge
+ * list getMST returns (ift.hpp:45-47) — a different, order-free object (see above). */
 IFTWT_API int iftwt_region_adjacency(iftwt_ctx* ctx, uint32_t* a, uint32_t* b, uint32_t* saddle, size_t capacity,
                            size_t* n_pairs);
 /* Region attributes, sorted by seed id: area = conquered vertices, height = max vertex
- * value (the order-free part of r_info, ift.hpp:5-23). */
+ * value (the order-free part of r_info, ift.hpp:5-23; `volume` is order dependent and not provided). */
 IFTWT_API int iftwt_region_info(iftwt_ctx* ctx, uint32_t* seed, uint32_t* area, float* height, size_t capacity,
                       size_t* n_regions);
 /* Cluster(mst, root_m, g_v, num_regions) + getLabelCloud (cluster.hpp:25-81): merge the
