@@ -63,6 +63,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS) + ["cfg4"])
+    ap.add_argument("--no-batch", action="store_true", help="skip the iftwt_batch_segment measurement (profiling runs)")
     ap.add_argument("--serial-headline", action="store_true",
                     help="report the one-ctx figure as `value` (default: the iftwt_batch_segment figure)")
     ap.add_argument("--lanes", type=int, default=0,
@@ -665,6 +666,8 @@ def main():
     lanes = args.lanes or (3 if args.workload == "cfg5" else 2)
     batch_info = None
     try:
+        if args.no_batch:
+            raise RuntimeError("skipped (--no-batch)")
         with api.Batch(local, lanes) as bt:
             nb = args.steps                                           # EXACTLY K steps = K clouds
             clouds = [(dev_ins[i % per_rank].data_ptr(), n) for i in range(max(nb, 2 * lanes))]
@@ -808,8 +811,8 @@ def main():
             "ift": ift,
             "batch": batch_info,
             "serial_one_ctx": {"value": value, "ms_per_step": ms_total / args.steps},
-            "stats": {kk: stats[kk] for kk in ("n_cells", "cell_size", "knn_fallback", "n_arcs", "rg_segments",
-                                                "rg_sweeps", "n_seeds", "ift_levels")},
+            "stats": {kk: stats[kk] for kk in ("n_cells", "cell_size", "density_spread", "knn_fallback", "n_arcs",
+                                                "rg_segments", "rg_sweeps", "n_seeds", "ift_levels")},
         }
         cpu = None
         if not args.no_cpu_baseline and world == 1:

@@ -45,7 +45,7 @@ class Stats(C.Structure):
     _fields_ = [("n_points", C.c_uint64), ("n_cells", C.c_uint64), ("cell_size", C.c_double),
                 ("knn_fallback", C.c_uint64), ("n_arcs", C.c_uint64), ("rg_segments", C.c_uint64),
                 ("rg_sweeps", C.c_uint64), ("n_seeds", C.c_uint64), ("ift_levels", C.c_uint64),
-                ("kernel_launches", C.c_uint64), ("device_bytes", C.c_uint64)]
+                ("kernel_launches", C.c_uint64), ("device_bytes", C.c_uint64), ("density_spread", C.c_double)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}

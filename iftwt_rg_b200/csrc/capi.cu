@@ -158,7 +158,7 @@ int iftwt_create(iftwt_ctx** out, int device) {
   c->sm_count = prop.multiProcessorCount;
   if (cudaSetDevice(device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaMallocHost(&c->h_scalars, 4096) != cudaSuccess) {
+      cudaMallocHost(&c->h_scalars, 4096) != cudaSuccess || cudaMallocHost(&c->h_hist, 17 * 256 * 4) != cudaSuccess) {
     g_err = std::string("ctx setup failed: ") + cudaGetErrorString(cudaGetLastError());
     delete c;
     return IFTWT_ERR_CUDA;
@@ -182,10 +182,11 @@ void iftwt_destroy(iftwt_ctx* c) {
                     &c->qb2, &c->nbr, &c->nd2, &c->kth, &c->fb_list, &c->g_off, &c->g_adj, &c->g_deg, &c->g_fwd,
                     &c->ow_mask, &c->nrm, &c->vx_keys, &c->vx_rows, &c->vx_cent, &c->vx_hk, &c->vx_hv, &c->ift_res, &c->ift_wf, &c->ift_node, &c->h_keys, &c->h_vals, &c->h_pairs, &c->h_seeds, &c->h_info,
                     &c->rg_rank, &c->rg_parent, &c->rg_label, &c->rg_aux, &c->rg_aux2, &c->rg_masks, &c->seeds, &c->ift_w,
-                    &c->ift_byw, &c->out_a, &c->out_b};
+                    &c->ift_byw, &c->out_a, &c->out_b, &c->occ_hist};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (c->h_scalars) cudaFreeHost(c->h_scalars);
+  if (c->h_hist) cudaFreeHost(c->h_hist);
   for (int s = 0; s < IFTWT_STAGE_COUNT; ++s) {
     cudaEventDestroy(c->ev0[s]);
     cudaEventDestroy(c->ev1[s]);
@@ -626,6 +627,7 @@ int iftwt_get_stats(iftwt_ctx* c, iftwt_stats* out) {
   TRY(check_ctx(c));
   if (!out) return ctx_fail(c, IFTWT_ERR_INVALID, "null out");
   *out = c->stats;
+  out->density_spread = c->stats_density_spread;
   return IFTWT_OK;
 }
 

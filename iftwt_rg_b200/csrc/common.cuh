@@ -60,6 +60,9 @@ struct iftwt_ctx {
   GridView grid{};
   DevBuf cell_key, cell_cnt, cell_start, hkeys, hvals;
   DevBuf qb2;      // float [n] squared one-ring completeness bound per sorted point
+  DevBuf occ_hist; // u32 [17][256] run-length histogram of the occupancy estimate (grid.cu)
+  void* h_hist = nullptr;  // pinned mirror
+  double stats_density_spread = 1.0;  // mean / 25th-percentile occupancy of the last grid build
 
   // --- knn ---
   int knn_k = 0;   // 0 = none

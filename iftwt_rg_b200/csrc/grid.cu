@@ -118,8 +118,12 @@ __device__ __forceinline__ u32 lower_bound_keys(const u64* __restrict__ a, u32 n
 // range of the sorted keys).  Unlike N / #occupied cells this is not dragged down by
 // the partially filled cells along surface boundaries, so it measures the density a
 // query actually sees.  sums[l] accumulates the run lengths, l = 0..16.
+// hist[l][b] additionally counts, for every 8th sample, the run length in OCC_BINS_PER_OCTAVE bins per octave:
+// the host reads a low percentile of the occupancy from it (density spread of the cloud, see grid_build).
+#define OCC_BINS_PER_OCTAVE 8
+#define OCC_BINS 256
 __global__ void occupancy_kernel(const u64* __restrict__ keys, u32 n, u32 stride, u32 n_samples,
-                                 unsigned long long* __restrict__ sums) {
+                                 unsigned long long* __restrict__ sums, u32* __restrict__ hist) {
   __shared__ unsigned long long sh[17];
   if (threadIdx.x < 17) sh[threadIdx.x] = 0ull;
   __syncthreads();
@@ -136,6 +140,10 @@ __global__ void occupancy_kernel(const u64* __restrict__ keys, u32 n, u32 stride
       lo = a;
       hi = b;
       atomicAdd(&sh[l], (unsigned long long)(hi - lo));
+      if ((s & 7u) == 0u && hi > lo) {
+        const int bin = min(OCC_BINS - 1, (int)((float)OCC_BINS_PER_OCTAVE * log2f((float)(hi - lo))));
+        atomicAdd(&hist[l * OCC_BINS + bin], 1u);
+      }
     }
   }
   __syncthreads();
@@ -271,9 +279,12 @@ int grid_build(iftwt_ctx* c, int k) {
     u32 stride = m / 65536u;
     if (stride == 0) stride = 1;
     u32 n_samples = (m + stride - 1) / stride;
-    LAUNCH(c, occupancy_kernel, div_up(n_samples, 128), 128, 0, k1, m, stride, n_samples, sums);
+    ENSURE(c, c->occ_hist, 17 * OCC_BINS * 4);
+    CU_TRY(c, cudaMemsetAsync(c->occ_hist.p, 0, 17 * OCC_BINS * 4, c->stream));
+    LAUNCH(c, occupancy_kernel, div_up(n_samples, 128), 128, 0, k1, m, stride, n_samples, sums, c->occ_hist.as<u32>());
     CHECK_LAUNCH(c);
     CU_TRY(c, cudaMemcpyAsync(hs + 80, sums, 17 * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(c->h_hist, c->occ_hist.p, 17 * OCC_BINS * 4, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     const unsigned long long* hh = (const unsigned long long*)(hs + 80);
     double ppc[17];
@@ -282,8 +293,44 @@ int grid_build(iftwt_ctx* c, int k) {
       ppc[l] = fmax(1.0, 1.0 + (double)sub * ((double)hh[l] / (double)n_samples - 1.0));
     // a Poisson-filled cell of mean occupancy m is seen by its own points as m + 1;
     // m = 0.45 k puts the k-th neighbour at about cell / 1.2 on a surface (swept on B200)
-    const double beta = env_double("IFTWT_PPC_PER_K", 0.45);
+    double beta = env_double("IFTWT_PPC_PER_K", 0.45);
     double target = beta * (double)(k < 2 ? 2 : k) + 1.0;
+    c->stats_density_spread = 1.0;
+    if (!getenv("IFTWT_PPC_PER_K") && env_double("IFTWT_PPC_ADAPT", 1.0) != 0.0 && n_samples >= 8192) {
+      // Density spread.  The mean above is carried by the DENSE parts of a cloud; where the density is a
+      // third of it (the ground plane of BASELINE configs 2 / 5 against its cylinder and sphere) the k-th
+      // neighbour lies outside the 3x3x3 block and the query leaves the fast path: 17.7 % of cfg5's queries,
+      // 0.9 of its 2.0 ms of k-NN.  One level above the cell scale — where a cell holds enough sampled points
+      // for the count to mean something — the ratio of the mean occupancy to its 25th percentile (both
+      // point-weighted) is 1.17 on the facade, 1.9 on the primitives scene, 1.7 on the statue.  At 1.35 or
+      // more the cell is sized for the sparse quarter instead: the occupancy target grows by that ratio
+      // (at most 2).  Swept on B200 (cfg5): beta 0.45 -> 5.35 ms per cloud, 0.7 -> 4.43, 0.85 -> 4.33,
+      // 1.0 -> 4.46; cfg3 keeps 0.45.  Any cell size gives the same, exact rows.
+      int l = 0;
+      while (l < 16 && ppc[l + 1] >= target) ++l;
+      const int L2 = l - 1;
+      if (L2 >= 1 && ppc[L2] >= 8.0) {
+        const u32* hh2 = (const u32*)c->h_hist + (size_t)L2 * OCC_BINS;
+        unsigned long long tot = 0;
+        for (int b = 0; b < OCC_BINS; ++b) tot += hh2[b];
+        if (tot >= 1024) {
+          unsigned long long acc = 0;
+          int b25 = 0;
+          for (; b25 < OCC_BINS; ++b25) {
+            acc += hh2[b25];
+            if (4 * acc >= tot) break;
+          }
+          const double run25 = exp2(((double)b25 + 0.5) / (double)OCC_BINS_PER_OCTAVE);
+          const double occ25 = fmax(1.0, 1.0 + (double)sub * (run25 - 1.0));
+          const double spread = ppc[L2] / occ25;
+          c->stats_density_spread = spread;
+          if (spread >= 1.35) {
+            beta *= fmin(spread, 2.0);
+            target = beta * (double)(k < 2 ? 2 : k) + 1.0;
+          }
+        }
+      }
+    }
     if (ppc[0] <= target) {
       cell = side;
     } else {

@@ -46,7 +46,8 @@ def measure(args, ctx, api, torch, dev, n, k, env):
     cost, label, ns = ctx.segment(k, k, rg)
     h = hashlib.sha256(cost.tobytes() + label.tobytes()).hexdigest()[:16]
     print(json.dumps({"env": env, "ms": round(ms, 4),
-                      "stage_ms": {s: round(v / args.steps, 4) for s, v in acc.items() if v}, "seeds": ns, "sha": h}),
+                      "stage_ms": {s: round(v / args.steps, 4) for s, v in acc.items() if v}, "seeds": ns, "sha": h,
+                      "stats": {kk: ctx.stats()[kk] for kk in ("cell_size", "density_spread", "knn_fallback")}}),
           flush=True)
 
 
