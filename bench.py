@@ -2,18 +2,30 @@
 """bench.py — IFT-WT segmentation throughput (BASELINE.json metric) on N B200s.
 
 A step = one pass of the hot path (k-NN graph, normals/curvature, region-growing
-seeds, IFT watershed) over one synthetic cloud per rank.
+seeds, IFT watershed) over one synthetic cloud; every rank runs K steps on its own clouds.
 
-  value     points/s, all ranks, cloud already resident in HBM when the timed
-            region starts, results left on the device (CUDA events, max over ranks)
+  value     points/s, all ranks, clouds already resident in HBM when the timed region starts,
+            results left on the device (CUDA events, max over ranks).  The K clouds go through
+            iftwt_batch_segment — 2 lanes (ctx + stream + host thread) on the GPU pulling from
+            one queue, so the latency-bound stretches of one cloud (227 small IFT levels) are filled
+            by the kernels of the other; every cloud still runs the whole pipeline.  The one-ctx,
+            one-cloud-at-a-time figure that the roofline and the stage times refer to is
+            detail.serial_one_ctx (--serial-headline makes it `value`).
   e2e       the same through the C ABI with HOST buffers: pinned host cloud in,
             host cost/label out, every step, inside the timed region
   roofline  the dominant kernel (k-NN fast path) against the measured HBM peak
   cpu_baseline  the CPU oracle (a port of the reference's CPU path; the reference as a
             whole cannot be built here) on a bounded sample of the same cloud, plus the
             reference's own ift.hpp (oracle/_ref) on a 20 k-point sample
+  detail.parity   GPU vs oracle on that sample, counted (cost / label mismatches, tie-only
+            disagreements with the reference's first-offer rule, the reference's own fixture)
+  detail.cfg5     BASELINE config 5 on the same GPUs: 64 clouds of 2 M points split over the ranks
+  detail.sharded  (N > 1) BASELINE config 4's shape: k-NN + normals sharded by Morton range with an
+            NCCL halo exchange inside libiftwt.so, rows verified against one GPU, then the whole
+            sharded segmentation (gather to rank 0, IFT there)
 
-`--impl reference` times that CPU path as the reference arm.
+`--workload cfg4` runs config 4 itself (100 M points, one iftwt_sharded_segment per step).
+`--impl reference` times the CPU path as the reference arm (thread count pinned to the cores).
 """
 from __future__ import annotations
 
@@ -67,7 +79,7 @@ def parse():
     ap.add_argument("--serial-headline", action="store_true",
                     help="report the one-ctx figure as `value` (default: the iftwt_batch_segment figure)")
     ap.add_argument("--lanes", type=int, default=0,
-                    help="lanes of the iftwt_batch measurement (0: 3 for cfg5, 2 otherwise)")
+                    help="lanes of the iftwt_batch measurement (0: 4 for cfg5, 2 otherwise; swept on B200)")
     ap.add_argument("--no-cfg5", action="store_true",
                     help="skip detail.cfg5 (BASELINE config 5's batch of 64 2M-point clouds split over the ranks)")
     ap.add_argument("--no-sharded", action="store_true",
@@ -663,7 +675,7 @@ def main():
 
     # iftwt_batch_segment: the same clouds through `lanes` ctxs (one stream + one host thread each) that pull
     # from one queue; every cloud still goes through the whole pipeline, results are iftwt_segment's
-    lanes = args.lanes or (3 if args.workload == "cfg5" else 2)
+    lanes = args.lanes or (4 if args.workload == "cfg5" else 2)
     batch_info = None
     try:
         if args.no_batch:
@@ -772,14 +784,24 @@ def main():
         alg_bytes = (16 + 4 * k) * n
         achieved = alg_bytes / (knn_ms * 1e-3) / 1e9 if knn_ms > 0 else 0.0
         traffic = None
+        issue_slot = None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json"))).get(args.workload)
             if tr and n == n_default and k == k_default:
                 traffic = int(tr["dram_bytes_read"]) + int(tr["dram_bytes_write"])
+                if tr.get("warp_instructions") and knn_ms > 0:
+                    # the limiter that is actually active: warp instructions issued (ncu smsp__inst_executed.sum of
+                    # the committed capture) against what the SMs can issue — 4 schedulers x 1 instruction per clock
+                    wi = float(tr["warp_instructions"])
+                    sm_clock = float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0) * 1e6
+                    rate = 148 * 4 * sm_clock
+                    issue_slot = {"warp_instructions_per_launch": int(wi), "warp_instructions_per_query": wi / n,
+                                  "issue_rate_warp_inst_per_s": rate, "floor_ms": 1e3 * wi / rate,
+                                  "frac": (1e3 * wi / rate) / knn_ms, "source": tr.get("source")}
         except Exception:
             pass
         roofline = {"bound": "hbm", "kernel": "knn_cell_kernel (first launch + the crowded-cell launch, one event pair)", "achieved": achieved, "peak": peak,
-                    "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
+                    "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic, "issue_slot": issue_slot,
                     "active_limiter": "instruction issue (ncu: 79 % issue-active, ALU pipe 63 %, LSU pipe 56 %, DRAM 7 %), not HBM",
                     "peak_source": which, "algorithmic_bytes_per_launch": alg_bytes,
                     "avg_launch_ms": knn_ms}
@@ -851,7 +873,7 @@ def main():
     ctx.close()
     if not args.no_cfg5 and args.workload == "cfg3":
         # BASELINE config 5 on the same GPUs: 64 clouds of 2 M points, 64 // N per rank through iftwt_batch_segment
-        # (3 lanes), no data-path collective.  At most 8 distinct clouds per rank are generated; the batch cycles.
+        # (4 lanes), no data-path collective.  At most 8 distinct clouds per rank are generated; the batch cycles.
         c5 = None
         try:
             n5, k5 = 2_000_000, 16
@@ -860,10 +882,10 @@ def main():
             dev5 = [torch.from_numpy(synth.scene_primitives(n5, seed=0x1F50 + rank * mine + i)).cuda()
                     for i in range(distinct)]
             rg5 = api.RgParams(RG_MIN, RG_MAX, k5, THETA, 1.0)
-            with api.Batch(local, 3) as bt:
+            with api.Batch(local, 4) as bt:
                 clouds = [(dev5[i % distinct].data_ptr(), n5) for i in range(mine)]
-                bt.segment(clouds[:6], k5, rg5, on_device=True)
-                bt.segment(clouds[:6], k5, rg5, on_device=True)
+                bt.segment(clouds[:8], k5, rg5, on_device=True)
+                bt.segment(clouds[:8], k5, rg5, on_device=True)
                 st0 = torch.cuda.ExternalStream(bt.ctx(0).stream(), device=torch.device("cuda", local))
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 barrier()
@@ -876,7 +898,7 @@ def main():
                     dist.all_reduce(ms5, op=dist.ReduceOp.MAX)
                 ms5 = float(ms5.item())
             c5 = {"workload": WORKLOADS["cfg5"][3], "clouds": mine * world, "clouds_per_gpu": mine,
-                  "distinct_clouds_per_gpu": distinct, "points_per_cloud": n5, "k": k5, "lanes": 3, "batch_ms": ms5,
+                  "distinct_clouds_per_gpu": distinct, "points_per_cloud": n5, "k": k5, "lanes": 4, "batch_ms": ms5,
                   "clouds_per_s": mine * world / (ms5 * 1e-3), "points_per_s": mine * world * n5 / (ms5 * 1e-3),
                   "points_per_s_per_gpu": mine * n5 / (ms5 * 1e-3), "seeds_first_cloud": int(seeds5[0]),
                   "what": "iftwt_batch_segment per rank, clouds resident in HBM, results left on the device"}
