@@ -99,7 +99,7 @@ def parse():
     ap.add_argument("--no-parity", action="store_true", help="skip detail.parity (GPU vs oracle on the cpu sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-inflight", type=int, default=2,
+    ap.add_argument("--e2e-inflight", type=int, default=3,
                     help="clouds in flight in the e2e measurement (one ctx + stream each)")
     return ap.parse_args()
 

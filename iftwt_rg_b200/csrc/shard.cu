@@ -214,42 +214,51 @@ __global__ void shard_kth_max_kernel(const float* __restrict__ d2, u32 m, int k,
   if ((threadIdx.x & 31) == 0 && b) atomicMax(&meta->kth_bits, b);
 }
 
-__global__ void shard_hist_kernel(const float4* __restrict__ pts, u32 n, CoarseGrid g, u32* __restrict__ hist) {
-  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = i < n;
-  const unsigned act = __ballot_sync(0xffffffffu, valid);
-  if (!valid) return;
-  int ix, iy, iz;
-  coarse_cell(g, pts[i], ix, iy, iz);
-  const u32 bin = (u32)(morton3((u32)ix, (u32)iy, (u32)iz) >> g.shift);
-  const unsigned grp = __match_any_sync(act, bin);
-  if ((int)(threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(&hist[bin], (u32)__popc(grp));
+// A slice that is a spatial tile falls into a few dozen bins: one global atomic per warp and bin serialised on
+// those few addresses (2 ms for 12.5 M points).  Each block therefore counts its 1,024 points in a small
+// shared-memory table first (open addressing on the bin) and flushes one atomic per distinct bin.
+#define HIST_SLOTS 2048
+__global__ void __launch_bounds__(256)
+shard_hist_kernel(const float4* __restrict__ pts, u32 n, CoarseGrid g, u32* __restrict__ hist) {
+  __shared__ u32 s_key[HIST_SLOTS];
+  __shared__ u32 s_cnt[HIST_SLOTS];
+  for (int t = threadIdx.x; t < HIST_SLOTS; t += 256) {
+    s_key[t] = 0xFFFFFFFFu;
+    s_cnt[t] = 0;
+  }
+  __syncthreads();
+  const u32 i0 = blockIdx.x * PACK_TILE + threadIdx.x;
+#pragma unroll
+  for (int q = 0; q < PACK_PPT; ++q) {
+    const u32 i = i0 + q * 256;
+    if (i >= n) break;
+    int ix, iy, iz;
+    coarse_cell(g, pts[i], ix, iy, iz);
+    const u32 bin = (u32)(morton3((u32)ix, (u32)iy, (u32)iz) >> g.shift);
+    u32 slot = (bin * 2654435761u) >> 21;  // 11 bits
+    while (true) {
+      const u32 prev = atomicCAS(&s_key[slot], 0xFFFFFFFFu, bin);
+      if (prev == 0xFFFFFFFFu || prev == bin) {
+        atomicAdd(&s_cnt[slot], 1u);
+        break;
+      }
+      slot = (slot + 1) & (HIST_SLOTS - 1);  // at most 1,024 distinct bins per block: the table never fills
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < HIST_SLOTS; t += 256)
+    if (s_cnt[t]) atomicAdd(&hist[s_key[t]], s_cnt[t]);
 }
 // owner_of_bin[b] = min(W - 1, points_before_b * W / total): contiguous Morton ranges, balanced to the
-// granularity of a bin.  One block; every rank computes the same table from the same histogram.
-__global__ void __launch_bounds__(1024)
-shard_owner_kernel(const u32* __restrict__ hist, u32 nbins, unsigned long long total, int W,
-                   unsigned char* __restrict__ owner) {
-  __shared__ unsigned long long s_part[1024];
-  const u32 per = (nbins + 1023u) / 1024u;
-  const u32 b0 = threadIdx.x * per, b1 = min(nbins, b0 + per);
-  unsigned long long sum = 0;
-  for (u32 b = b0; b < b1; ++b) sum += hist[b];
-  s_part[threadIdx.x] = sum;
-  __syncthreads();
-  // exclusive scan of the 1024 partial sums (Hillis-Steele in shared memory)
-  for (int o = 1; o < 1024; o <<= 1) {
-    unsigned long long t = threadIdx.x >= (u32)o ? s_part[threadIdx.x - o] : 0ull;
-    __syncthreads();
-    s_part[threadIdx.x] += t;
-    __syncthreads();
-  }
-  unsigned long long before = s_part[threadIdx.x] - sum;
-  for (u32 b = b0; b < b1; ++b) {
-    unsigned long long o = total ? before * (unsigned long long)W / total : 0ull;
-    owner[b] = (unsigned char)min(o, (unsigned long long)(W - 1));
-    before += hist[b];
-  }
+// granularity of a bin; every rank computes the same table from the same histogram.  `before` is the exclusive
+// scan of the histogram (CUB); a single-block scan of the 2^18 bins took 0.57 ms — a quarter of the partition
+// phase (profiles/r02_shard_kernels_ncu_full.txt).
+__global__ void shard_owner_kernel(const u32* __restrict__ before, u32 nbins, unsigned long long total, int W,
+                                   unsigned char* __restrict__ owner) {
+  const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbins) return;
+  const unsigned long long o = total ? (unsigned long long)before[b] * (unsigned long long)W / total : 0ull;
+  owner[b] = (unsigned char)min(o, (unsigned long long)(W - 1));
 }
 
 // route word of a point: bits 0..7 destination mask (owner included), bits 16..19 owner
@@ -257,18 +266,31 @@ __device__ __forceinline__ u32 route_of(const CoarseGrid& g, const unsigned char
                                         const float4 p) {
   int ix, iy, iz;
   coarse_cell(g, p, ix, iy, iz);
-  const u32 own = owner_of_bin[(u32)(morton3((u32)ix, (u32)iy, (u32)iz) >> g.shift)];
-  u32 mask = 1u << own;
-  const int x0 = max(ix - 1, 0), x1 = min(ix + 1, g.dx - 1);
-  const int y0 = max(iy - 1, 0), y1 = min(iy + 1, g.dy - 1);
-  const int z0 = max(iz - 1, 0), z1 = min(iz + 1, g.dz - 1);
-  // interior of a bin-aligned box: all 27 cells lie in the point's own bin
+  // shift = 3 hbits, so the bin of a cell is the Morton code of (ix >> h, iy >> h, iz >> h): the 27 cells of
+  // the block fall into at most 2 x 2 x 2 bins — the own one and, per axis, the one a step across the nearer
+  // face of the bin-aligned box leads to, if the cell touches that face (and the grid continues there).
+  // (27 cell lookups per point near a face were 65 % issue-active and 1 ms per 12.5 M points.)
   const int h = g.hbits;
-  if (!((x0 >> h) == (x1 >> h) && (y0 >> h) == (y1 >> h) && (z0 >> h) == (z1 >> h))) {
-    for (int z = z0; z <= z1; ++z)
-      for (int y = y0; y <= y1; ++y)
-        for (int x = x0; x <= x1; ++x)
-          mask |= 1u << owner_of_bin[(u32)(morton3((u32)x, (u32)y, (u32)z) >> g.shift)];
+  const int bx = ix >> h, by = iy >> h, bz = iz >> h;
+  const u32 own = owner_of_bin[(u32)morton3((u32)bx, (u32)by, (u32)bz)];
+  u32 mask = 1u << own;
+  const int m = (1 << h) - 1;
+  // candidate bin offsets per axis: 0 always; -1 / +1 when the neighbouring CELL lies in the neighbouring bin
+  int ox[3], oy[3], oz[3], nx = 1, ny = 1, nz = 1;
+  ox[0] = oy[0] = oz[0] = 0;
+  if ((ix & m) == 0 && ix > 0) ox[nx++] = -1;
+  if ((ix & m) == m && ix < g.dx - 1) ox[nx++] = 1;
+  if ((iy & m) == 0 && iy > 0) oy[ny++] = -1;
+  if ((iy & m) == m && iy < g.dy - 1) oy[ny++] = 1;
+  if ((iz & m) == 0 && iz > 0) oz[nz++] = -1;
+  if ((iz & m) == m && iz < g.dz - 1) oz[nz++] = 1;
+  if (nx + ny + nz > 3) {
+    for (int a = 0; a < nz; ++a)
+      for (int b = 0; b < ny; ++b)
+        for (int c = 0; c < nx; ++c) {
+          if ((a | b | c) == 0) continue;
+          mask |= 1u << owner_of_bin[(u32)morton3((u32)(bx + ox[c]), (u32)(by + oy[b]), (u32)(bz + oz[a]))];
+        }
   }
   return mask | (own << 16);
 }
@@ -422,6 +444,27 @@ __global__ void shard_export_rows_kernel(const u32* __restrict__ owned_idx, u32 
   o_knn[e] = sid == SID_NONE ? -1 : (int)gid_sorted[sid];
   o_d2[e] = nd2[src];
 }
+// the same, four entries per thread (k a multiple of 4: rows are 16-byte aligned on both sides): 16-byte loads and
+// stores, four gathers in flight per thread (one entry per thread moved 274 MB per million rows at 2.3 TB/s)
+__global__ void shard_export_rows4_kernel(const u32* __restrict__ owned_idx, u32 n_owned, int k4 /* k / 4 */,
+                                          const u32* __restrict__ gid_sorted, const u32* __restrict__ inv,
+                                          const uint4* __restrict__ nbr4, const float4* __restrict__ nd24,
+                                          int4* __restrict__ o_knn4, float4* __restrict__ o_d24) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (size_t)n_owned * k4) return;
+  const u32 j = (u32)(e / (u32)k4);
+  const int col = (int)(e - (size_t)j * k4);
+  const size_t src = (size_t)inv[owned_idx[j]] * k4 + col;
+  const uint4 v = nbr4[src];
+  const float4 d = nd24[src];
+  int4 o;
+  o.x = v.x == SID_NONE ? -1 : (int)gid_sorted[v.x];
+  o.y = v.y == SID_NONE ? -1 : (int)gid_sorted[v.y];
+  o.z = v.z == SID_NONE ? -1 : (int)gid_sorted[v.z];
+  o.w = v.w == SID_NONE ? -1 : (int)gid_sorted[v.w];
+  o_knn4[e] = o;
+  o_d24[e] = d;
+}
 
 // ---- gather to the root (iftwt_sharded_segment) ------------------------------------------------
 __global__ void shard_pos_of_gid_kernel(const u32* __restrict__ gid, u32 n, u32* __restrict__ pos_of_gid,
@@ -465,7 +508,7 @@ struct Shard {
   iftwt_ctx* ctx = nullptr;       // local compute; its stream carries everything this shard does
   ncclComm_t nccl = nullptr;
   void* h_pin = nullptr;          // pinned scratch (4 KB)
-  DevBuf meta, meta_all, hist, owner, route, blk, blk_off, send_pts, send_gid, recv_gid, cnt, cnt_all, flag, pos,
+  DevBuf meta, meta_all, hist, hist_scan, owner, route, blk, blk_off, send_pts, send_gid, recv_gid, cnt, cnt_all, flag, pos,
       owned_idx, small, sample_q, sample_d2, sample_idx;
   DevBuf o_gid, o_pts, o_knn, o_d2, o_nrm;             // results of iftwt_sharded_knn_normals
   DevBuf g_gid, g_pts, g_knn, g_d2, g_nrm, g_pos;       // root: gathered rows (iftwt_sharded_segment)
@@ -630,7 +673,7 @@ void shard_free(Shard& s) {
   if (!s.ctx) return;
   cudaSetDevice(s.device);
   cudaStreamSynchronize(s.ctx->stream);
-  DevBuf* bufs[] = {&s.meta, &s.meta_all, &s.hist, &s.owner, &s.route, &s.blk, &s.blk_off, &s.send_pts, &s.send_gid,
+  DevBuf* bufs[] = {&s.meta, &s.meta_all, &s.hist, &s.hist_scan, &s.owner, &s.route, &s.blk, &s.blk_off, &s.send_pts, &s.send_gid,
                     &s.recv_gid, &s.cnt, &s.cnt_all, &s.flag, &s.pos, &s.owned_idx, &s.small, &s.sample_q, &s.sample_d2,
                     &s.sample_idx, &s.o_gid, &s.o_pts, &s.o_knn, &s.o_d2, &s.o_nrm, &s.g_gid, &s.g_pts, &s.g_knn,
                     &s.g_d2, &s.g_nrm, &s.g_pos};
@@ -775,7 +818,8 @@ static int sharded_knn_normals_impl(iftwt_comm* cm, const iftwt_shard_in* in, in
       SH_ENSURE(cm, s, s.owner, (size_t)g.nbins);
       CM_CU(cm, cudaMemsetAsync(s.hist.p, 0, (size_t)g.nbins * 4, s.ctx->stream));
       const u32 n = (u32)in[l].n;
-      if (n) SH_LAUNCH(s, shard_hist_kernel, div_up(n, 256), 256, (const float4*)in[l].d_points, n, g, s.hist.as<u32>());
+      if (n)
+        SH_LAUNCH(s, shard_hist_kernel, div_up(n, PACK_TILE), 256, (const float4*)in[l].d_points, n, g, s.hist.as<u32>());
       histp[l] = s.hist.as<u32>();
     }
     TRY(coll_allreduce_sum_u32(cm, histp, g.nbins));
@@ -786,8 +830,18 @@ static int sharded_knn_normals_impl(iftwt_comm* cm, const iftwt_shard_in* in, in
       CM_CU(cm, cudaSetDevice(s.device));
       const u32 n = (u32)in[l].n;
       const float4* pts = (const float4*)in[l].d_points;
-      SH_LAUNCH(s, shard_owner_kernel, 1, 1024, (const u32*)s.hist.as<u32>(), g.nbins, (unsigned long long)n_total, W,
-                s.owner.as<unsigned char>());
+      {
+        SH_ENSURE(cm, s, s.hist_scan, (size_t)g.nbins * 4);
+        size_t tb = 0;
+        CM_CU(cm, cub::DeviceScan::ExclusiveSum(nullptr, tb, s.hist.as<u32>(), s.hist_scan.as<u32>(), (int)g.nbins,
+                                                s.ctx->stream));
+        SH_ENSURE(cm, s, s.ctx->tmp, tb);
+        CM_CU(cm, cub::DeviceScan::ExclusiveSum(s.ctx->tmp.p, tb, s.hist.as<u32>(), s.hist_scan.as<u32>(), (int)g.nbins,
+                                                s.ctx->stream));
+        s.ctx->stats.kernel_launches += 2;
+        SH_LAUNCH(s, shard_owner_kernel, div_up(g.nbins, 256), 256, (const u32*)s.hist_scan.as<u32>(), g.nbins,
+                  (unsigned long long)n_total, W, s.owner.as<unsigned char>());
+      }
       nblk[l] = n ? div_up(n, PACK_TILE) : 0;
       const size_t nb = nblk[l];
       SH_ENSURE(cm, s, s.route, ((size_t)n + 1) * 4);
@@ -912,9 +966,14 @@ static int sharded_knn_normals_impl(iftwt_comm* cm, const iftwt_shard_in* in, in
         u32* gid_sorted = s.flag.as<u32>();  // the flags are consumed: their buffer is reused
         SH_LAUNCH(s, shard_gid_sorted_kernel, div_up(m, 256), 256, (const u32*)s.recv_gid.as<u32>(),
                   (const u32*)c->perm.as<u32>(), (u32)m, gid_sorted);
-        SH_LAUNCH(s, shard_export_rows_kernel, div_up(no * k, 256), 256, (const u32*)s.owned_idx.as<u32>(), (u32)no, k,
-                  (const u32*)gid_sorted, (const u32*)c->inv.as<u32>(), (const u32*)c->nbr.as<u32>(),
-                  (const float*)c->nd2.as<float>(), s.o_knn.as<int>(), s.o_d2.as<float>());
+        if (k % 4 == 0)
+          SH_LAUNCH(s, shard_export_rows4_kernel, div_up(no * (k / 4), 256), 256, (const u32*)s.owned_idx.as<u32>(),
+                    (u32)no, k / 4, (const u32*)gid_sorted, (const u32*)c->inv.as<u32>(), (const uint4*)c->nbr.as<uint4>(),
+                    (const float4*)c->nd2.as<float4>(), s.o_knn.as<int4>(), s.o_d2.as<float4>());
+        else
+          SH_LAUNCH(s, shard_export_rows_kernel, div_up(no * k, 256), 256, (const u32*)s.owned_idx.as<u32>(), (u32)no, k,
+                    (const u32*)gid_sorted, (const u32*)c->inv.as<u32>(), (const u32*)c->nbr.as<u32>(),
+                    (const float*)c->nd2.as<float>(), s.o_knn.as<int>(), s.o_d2.as<float>());
       }
       CM_CU(cm, cudaGetLastError());
       cudaEventRecord(s.ev[5], c->stream);
