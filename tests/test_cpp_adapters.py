@@ -124,3 +124,14 @@ def test_adapters_reproduce_the_reference_own_classes(tmp_path, name):
     assert sha(out / "cost.u32") == g["ift"]["cost_sha256"]
     assert sha(out / "after_pc_to_g.f32") == g["values_after_pc_to_g_sha256"]
     assert sha(out / "erode_gradient.f32") == g["erode_gradient_sha256"]
+
+
+def test_batch_host_compiles(tmp_path):
+    assert os.path.exists(_build_cpp(tmp_path, "batch_test"))
+
+
+@pytest.mark.gpu
+def test_batch_from_a_plain_cpp_host(tmp_path):
+    """iftwt_batch_* called from C++ with host buffers (no torch, no CUDA headers): equal to one ctx, cloud by cloud."""
+    out = subprocess.run([_build_cpp(tmp_path, "batch_test")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "batch ok" in out.stdout, out.stdout + out.stderr
