@@ -75,3 +75,8 @@ def test_no_gpu_means_loud_failure_not_fallback():
         api.Context(0)
     assert e.value.code == -2
     assert "no CPU fallback" in str(e.value)
+    # the batch and the multi-GPU entry points fail the same way: no device, no fallback
+    for make in (lambda: api.Batch(0, 2), lambda: api.Comm.all([0, 0]), lambda: api.Comm.all([0])):
+        with pytest.raises(api.IftwtError) as e:
+            make()
+        assert e.value.code == -2 and "no CPU fallback" in str(e.value)
