@@ -551,6 +551,16 @@ int comm_fail(iftwt_comm* cm, int code, const char* fmt, ...) {
       return comm_fail((cm), IFTWT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, g_nccl.GetErrorString(_r), \
                        __FILE__, __LINE__);                                                     \
   } while (0)
+// inside ncclGroupStart / ncclGroupEnd: a failure closes the group before it is reported
+#define CM_NCCL_G(cm, expr)                                                                     \
+  do {                                                                                          \
+    ncclResult_t _r = (expr);                                                                   \
+    if (_r != ncclSuccess) {                                                                    \
+      g_nccl.GroupEnd();                                                                        \
+      return comm_fail((cm), IFTWT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, g_nccl.GetErrorString(_r), \
+                       __FILE__, __LINE__);                                                     \
+    }                                                                                           \
+  } while (0)
 // a stage function of the shard's ctx failed: its message becomes the comm's
 #define CM_CTX(cm, s, expr)                                                       \
   do {                                                                            \
@@ -584,7 +594,7 @@ int coll_allgather(iftwt_comm* cm, const std::vector<const void*>& send, const s
   CM_NCCL(cm, g_nccl.GroupStart());
   for (size_t a = 0; a < cm->sh.size(); ++a) {
     CM_CU(cm, cudaSetDevice(cm->sh[a].device));
-    CM_NCCL(cm, g_nccl.AllGather(send[a], recv[a], bytes, ncclUint8, cm->sh[a].nccl, cm->sh[a].ctx->stream));
+    CM_NCCL_G(cm, g_nccl.AllGather(send[a], recv[a], bytes, ncclUint8, cm->sh[a].nccl, cm->sh[a].ctx->stream));
   }
   CM_NCCL(cm, g_nccl.GroupEnd());
   return IFTWT_OK;
@@ -603,7 +613,7 @@ int coll_allreduce_sum_u32(iftwt_comm* cm, const std::vector<u32*>& buf, size_t 
   CM_NCCL(cm, g_nccl.GroupStart());
   for (size_t a = 0; a < cm->sh.size(); ++a) {
     CM_CU(cm, cudaSetDevice(cm->sh[a].device));
-    CM_NCCL(cm, g_nccl.AllReduce(buf[a], buf[a], count, ncclUint32, ncclSum, cm->sh[a].nccl, cm->sh[a].ctx->stream));
+    CM_NCCL_G(cm, g_nccl.AllReduce(buf[a], buf[a], count, ncclUint32, ncclSum, cm->sh[a].nccl, cm->sh[a].ctx->stream));
   }
   CM_NCCL(cm, g_nccl.GroupEnd());
   return IFTWT_OK;
@@ -647,10 +657,10 @@ int coll_alltoallv(iftwt_comm* cm, const std::vector<A2APayload>& pay, const std
           continue;
         }
         if (cs)
-          CM_NCCL(cm, g_nccl.Send((const char*)p.send[a] + send_off[a][r] * p.elem, cs * p.elem, ncclUint8, r, s.nccl,
+          CM_NCCL_G(cm, g_nccl.Send((const char*)p.send[a] + send_off[a][r] * p.elem, cs * p.elem, ncclUint8, r, s.nccl,
                                   s.ctx->stream));
         if (cr)
-          CM_NCCL(cm, g_nccl.Recv((char*)p.recv[a] + recv_off[a][r] * p.elem, cr * p.elem, ncclUint8, r, s.nccl,
+          CM_NCCL_G(cm, g_nccl.Recv((char*)p.recv[a] + recv_off[a][r] * p.elem, cr * p.elem, ncclUint8, r, s.nccl,
                                   s.ctx->stream));
       }
     }
