@@ -365,7 +365,7 @@ class ShardedRun:
                                             "knn_cell_kernel": mx[5]},
                 "halo_bytes_over_nvlink": int(sm[0]), "exchange_bytes_over_nvlink": int(sm[1]),
                 "owned_per_rank": per[0::2], "halo_per_rank": per[1::2], "halo_fraction": sm[3] / max(sm[2], 1.0),
-                "halo_radius": o.halo_radius, "attempts": o.attempts}
+                "halo_radius": o.halo_radius, "attempts": o.attempts, "peer_to_peer": int(o.peer_to_peer)}
 
     def verify(self, o, target_rows=1_000_000):
         """A sample of every rank's rows against ONE GPU holding the whole cloud: rank 0 answers the sampled
@@ -451,9 +451,11 @@ def sharded_detail(args, torch, dist, api, world, rank, local, n_total, k, tiles
         if ver:
             out.update(ver)
         run.segment()                                   # warm-up: allocations on the root
+        run.segment()                                   # ... which the peers map at the start of this call
         ms_seg, res = run.timed(lambda: run.segment())
         st = run.ctx.stats() if rank == 0 else {}
         out["segment_ms"] = ms_seg
+        out["segment_peer_to_peer"] = int(res[3][0].peer_to_peer)
         out["segment_points_per_s"] = n_total / (ms_seg * 1e-3)
         out["segment_what"] = "iftwt_sharded_segment: the above + rows gathered to rank 0 (NCCL), graph / seeds / IFT there"
         if rank == 0:
@@ -1018,7 +1020,7 @@ def main_cfg4(args):
             "cpu_baseline": None,
             "detail": {"sharded_knn_normals": dict({"ms": ms_knn, "points_per_s": n_total / (ms_knn * 1e-3),
                                                     "first_call": run.first}, **phases, **(ver or {})),
-                       "root_stage_ms": root_stage,
+                       "root_stage_ms": root_stage, "segment_peer_to_peer": int(res[3][0].peer_to_peer),
                        "root_stats": {kk: root_stats[kk] for kk in ("n_arcs", "n_seeds", "ift_levels", "rg_segments")},
                        "seeds": int(res[2])},
         }

@@ -64,7 +64,7 @@ class ShardOut(C.Structure):
                 ("kth_distance_max", C.c_double), ("halo_bytes_sent", C.c_uint64),
                 ("exchange_bytes_sent", C.c_uint64), ("ms_estimate", C.c_float), ("ms_partition", C.c_float),
                 ("ms_exchange", C.c_float), ("ms_compute", C.c_float), ("ms_export", C.c_float),
-                ("knn_cell_ms", C.c_float)]
+                ("knn_cell_ms", C.c_float), ("peer_to_peer", C.c_int)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_ if not f.startswith("d_")}

@@ -42,6 +42,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <new>
 #include <string>
@@ -142,11 +143,12 @@ struct ShardMeta {
   u32 n;                 // points in the slice
   u32 gid0;              // global id of its first point
   u32 kth_bits;          // float bits: upper bound estimate of the k-th neighbour distance^2 (0 = none)
-  u32 pad[6];
+  u32 epoch;             // bumped whenever one of the rank's peer-writable buffers is (re)allocated
+  u32 pad[5];
 };
 static_assert(sizeof(ShardMeta) == 64, "ShardMeta is one 64-byte record");
 
-__global__ void shard_meta_init_kernel(ShardMeta* m, u32 n, u32 gid0) {
+__global__ void shard_meta_init_kernel(ShardMeta* m, u32 n, u32 gid0, u32 epoch) {
   if (threadIdx.x == 0) {
     for (int a = 0; a < 3; ++a) {
       m->lo[a] = 0x7FFFFFFF;
@@ -156,7 +158,8 @@ __global__ void shard_meta_init_kernel(ShardMeta* m, u32 n, u32 gid0) {
     m->n = n;
     m->gid0 = gid0;
     m->kth_bits = 0;
-    for (int a = 0; a < 6; ++a) m->pad[a] = 0;
+    m->epoch = epoch;
+    for (int a = 0; a < 5; ++a) m->pad[a] = 0;
   }
 }
 __global__ void shard_bbox_kernel(const float4* __restrict__ pts, u32 n, ShardMeta* __restrict__ m) {
@@ -333,10 +336,18 @@ shard_route_kernel(const float4* __restrict__ pts, u32 n, CoarseGrid g,
 }
 // pass 2: every point is written once per destination, at a position that preserves the input order
 // inside each destination's run
+// Where the run of destination d starts: in the local send buffer (NCCL exchange: pts[d] = the send buffer,
+// base[d] = first record of d's run) or — peer-to-peer exchange — straight in rank d's receive buffer over
+// NVLink (pts[d] / gid[d] = that buffer as mapped on this device, base[d] = where this source's block starts
+// in it): the pack kernel IS the exchange then, no send buffer, no NCCL transfer.
+struct PackDst {
+  float4* pts[SHARD_MAX_RANKS];
+  u32* gid[SHARD_MAX_RANKS];
+  u32 base[SHARD_MAX_RANKS];
+};
 __global__ void __launch_bounds__(256)
 shard_pack_kernel(const float4* __restrict__ pts, u32 n, u32 gid0, const u32* __restrict__ route,
-                  const u32* __restrict__ blk_off, u32 nblk, int W, float4* __restrict__ send_pts,
-                  u32* __restrict__ send_gid) {
+                  const u32* __restrict__ blk_off, u32 nblk, int W, PackDst dst) {
   __shared__ u32 s_cnt[SHARD_MAX_RANKS][8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const u32 i0 = blockIdx.x * PACK_TILE + threadIdx.x * PACK_PPT;
@@ -364,13 +375,16 @@ shard_pack_kernel(const float4* __restrict__ pts, u32 n, u32 gid0, const u32* __
 #pragma unroll
   for (int d = 0; d < SHARD_MAX_RANKS; ++d) {
     if (d >= W) continue;
-    u32 pos = blk_off[(size_t)d * nblk + blockIdx.x] + excl[d];
+    // position inside d's run (the scan is over the destination-major count array) + where the run goes
+    u32 pos = dst.base[d] + (blk_off[(size_t)d * nblk + blockIdx.x] - blk_off[(size_t)d * nblk]) + excl[d];
     for (int w = 0; w < warp; ++w) pos += s_cnt[d][w];
+    float4* __restrict__ dp = dst.pts[d];
+    u32* __restrict__ dg = dst.gid[d];
 #pragma unroll
     for (int q = 0; q < PACK_PPT; ++q) {
       if ((r[q] >> d) & 1u) {
-        send_pts[pos] = pts[i0 + q];
-        send_gid[pos] = (gid0 + i0 + q) | ((r[q] >> 16) == (u32)d ? GID_OWNED : 0u);
+        dp[pos] = pts[i0 + q];
+        dg[pos] = (gid0 + i0 + q) | ((r[q] >> 16) == (u32)d ? GID_OWNED : 0u);
         ++pos;
       }
     }
@@ -502,23 +516,59 @@ __global__ void shard_sum_u32_kernel(u32* __restrict__ dst, const u32* __restric
 }  // namespace
 
 // ---- the communicator --------------------------------------------------------------------------
+// Buffers that PEERS write into directly over NVLink (cudaIpc mappings between processes, peer access inside
+// one): the receive buffers of the exchange and, on the root of iftwt_sharded_segment, the gathered rows.  A
+// buffer a peer may still have mapped is never freed before the comm is destroyed: growing one allocates a new
+// one, retires the old one to the graveyard and bumps the shard's epoch, which every rank sees in phase A of the
+// next call and answers with a fresh exchange of handles.
+enum { PB_RX_PTS = 0, PB_RX_GID, PB_G_GID, PB_G_PTS, PB_G_KNN, PB_G_D2, PB_G_NRM, PB_COUNT };
+struct PeerBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+struct PeerRecord {  // what a rank tells the others about its peer-writable buffers
+  cudaIpcMemHandle_t handle[PB_COUNT];
+  unsigned long long raw[PB_COUNT];  // the owner's own pointer (what a shard of the same process uses)
+  unsigned long long cap[PB_COUNT];
+  u32 epoch;
+  int pid;
+  int device;
+  u32 pad;
+};
+struct PeerView {  // a rank's buffers as THIS shard can address them
+  void* p[PB_COUNT] = {};
+  size_t cap[PB_COUNT] = {};
+  u32 epoch = 0xFFFFFFFFu;
+  bool ok = false;
+};
+struct IpcMapping {
+  cudaIpcMemHandle_t handle;
+  void* ptr;
+};
 struct Shard {
   int rank = 0;
   int device = 0;
   iftwt_ctx* ctx = nullptr;       // local compute; its stream carries everything this shard does
   ncclComm_t nccl = nullptr;
   void* h_pin = nullptr;          // pinned scratch (4 KB)
-  DevBuf meta, meta_all, hist, hist_scan, owner, route, blk, blk_off, send_pts, send_gid, recv_gid, cnt, cnt_all, flag, pos,
-      owned_idx, small, sample_q, sample_d2, sample_idx;
+  DevBuf meta, meta_all, hist, hist_scan, owner, route, blk, blk_off, send_pts, send_gid, cnt, cnt_all, flag, pos,
+      owned_idx, small, sample_q, sample_d2, sample_idx, peer_rec, peer_rec_all;
   DevBuf o_gid, o_pts, o_knn, o_d2, o_nrm;             // results of iftwt_sharded_knn_normals
-  DevBuf g_gid, g_pts, g_knn, g_d2, g_nrm, g_pos;       // root: gathered rows (iftwt_sharded_segment)
+  DevBuf g_pos;                                        // root: where each gathered row sits
+  PeerBuf pb[PB_COUNT];                                // rx_* : received points / ids; g_* : root's gathered rows
+  u32 epoch = 0;
+  std::vector<void*> graveyard;
+  PeerView view[SHARD_MAX_RANKS];
+  std::vector<IpcMapping> mapped;
   cudaEvent_t ev[6] = {};
   iftwt_shard_out out{};
   size_t m_total = 0, n_owned = 0;
+  bool exported_to_root = false;  // the last export wrote straight into the root's gathered-row buffers
 };
 struct iftwt_comm {
   int nranks = 0;
   bool loopback = false;          // every shard on one device, collectives are device-to-device copies
+  bool p2p = true;                // peers' buffers are addressable (settled by peers_refresh)
   std::vector<Shard> sh;          // the LOCAL shards (one in the process-per-GPU mode)
   std::string err;
 };
@@ -684,11 +734,16 @@ void shard_free(Shard& s) {
   cudaSetDevice(s.device);
   cudaStreamSynchronize(s.ctx->stream);
   DevBuf* bufs[] = {&s.meta, &s.meta_all, &s.hist, &s.hist_scan, &s.owner, &s.route, &s.blk, &s.blk_off, &s.send_pts, &s.send_gid,
-                    &s.recv_gid, &s.cnt, &s.cnt_all, &s.flag, &s.pos, &s.owned_idx, &s.small, &s.sample_q, &s.sample_d2,
-                    &s.sample_idx, &s.o_gid, &s.o_pts, &s.o_knn, &s.o_d2, &s.o_nrm, &s.g_gid, &s.g_pts, &s.g_knn,
-                    &s.g_d2, &s.g_nrm, &s.g_pos};
+                    &s.cnt, &s.cnt_all, &s.flag, &s.pos, &s.owned_idx, &s.small, &s.sample_q, &s.sample_d2,
+                    &s.sample_idx, &s.peer_rec, &s.peer_rec_all, &s.o_gid, &s.o_pts, &s.o_knn, &s.o_d2, &s.o_nrm, &s.g_pos};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
+  for (IpcMapping& m : s.mapped) cudaIpcCloseMemHandle(m.ptr);
+  s.mapped.clear();
+  for (PeerBuf& b : s.pb)
+    if (b.p) cudaFree(b.p);
+  for (void* g : s.graveyard) cudaFree(g);
+  s.graveyard.clear();
   if (s.h_pin) cudaFreeHost(s.h_pin);
   for (cudaEvent_t& e : s.ev)
     if (e) cudaEventDestroy(e);
@@ -704,11 +759,140 @@ void ctx_adopt_cloud(iftwt_ctx* c, size_t m) {
   c->stats.n_points = m;
 }
 
+// grow-only; the old buffer is retired, not freed (a peer may have it mapped)
+int peer_ensure(iftwt_comm* cm, Shard& s, int which, size_t bytes) {
+  PeerBuf& b = s.pb[which];
+  if (bytes <= b.cap) return IFTWT_OK;
+  const size_t want = bytes + bytes / 4 + 4096;
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) return comm_fail(cm, IFTWT_ERR_CUDA, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+  if (b.p) s.graveyard.push_back(b.p);
+  b.p = p;
+  b.cap = want;
+  ++s.epoch;
+  return IFTWT_OK;
+}
+
+// Collective: every rank publishes handles / pointers / capacities of its peer-writable buffers, every shard
+// maps what it does not share an address space with.  Called when some rank's epoch moved (phase A).
+int peers_refresh(iftwt_comm* cm) {
+  const int W = cm->nranks;
+  const size_t L = cm->sh.size();
+  std::vector<const void*> sendp(L);
+  std::vector<void*> recvp(L);
+  std::vector<PeerRecord> mine(L);
+  for (size_t l = 0; l < L; ++l) {
+    Shard& s = cm->sh[l];
+    CM_CU(cm, cudaSetDevice(s.device));
+    PeerRecord& r = mine[l];
+    memset(&r, 0, sizeof r);
+    r.epoch = s.epoch;
+    r.pid = (int)getpid();
+    r.device = s.device;
+    for (int b = 0; b < PB_COUNT; ++b) {
+      r.raw[b] = (unsigned long long)(uintptr_t)s.pb[b].p;
+      r.cap[b] = s.pb[b].cap;
+      if (s.pb[b].p && (int)L < W) {  // other processes exist: they need a handle
+        if (cudaIpcGetMemHandle(&r.handle[b], s.pb[b].p) != cudaSuccess) {
+          cudaGetLastError();
+          r.raw[b] = 0;  // cannot be shared: peers see no buffer here and keep to NCCL
+          r.cap[b] = 0;
+        }
+      }
+    }
+    SH_ENSURE(cm, s, s.peer_rec, sizeof(PeerRecord));
+    SH_ENSURE(cm, s, s.peer_rec_all, sizeof(PeerRecord) * W);
+    CM_CU(cm, cudaMemcpyAsync(s.peer_rec.p, &r, sizeof r, cudaMemcpyHostToDevice, s.ctx->stream));
+    sendp[l] = s.peer_rec.p;
+    recvp[l] = s.peer_rec_all.p;
+  }
+  TRY(sync_all(cm));  // `mine` is pageable: the copies above have read it
+  TRY(coll_allgather(cm, sendp, recvp, sizeof(PeerRecord)));
+  std::vector<PeerRecord> all(W);
+  {
+    Shard& s = cm->sh[0];
+    CM_CU(cm, cudaSetDevice(s.device));
+    CM_CU(cm, cudaMemcpyAsync(all.data(), s.peer_rec_all.p, sizeof(PeerRecord) * W, cudaMemcpyDeviceToHost, s.ctx->stream));
+    TRY(sync_all(cm));
+  }
+  u32 ok_local = 1;
+  for (size_t l = 0; l < L; ++l) {
+    Shard& s = cm->sh[l];
+    CM_CU(cm, cudaSetDevice(s.device));
+    for (int r = 0; r < W; ++r) {
+      PeerView& v = s.view[r];
+      const PeerRecord& rec = all[r];
+      const Shard* local = nullptr;
+      for (const Shard& t : cm->sh)
+        if (t.rank == r) local = &t;
+      v.ok = true;
+      for (int b = 0; b < PB_COUNT; ++b) {
+        v.p[b] = nullptr;
+        v.cap[b] = 0;
+        if (!rec.raw[b]) continue;
+        if (local) {
+          if (local->device != s.device) {  // same process, another GPU: peer access, once
+            cudaError_t e = cudaDeviceEnablePeerAccess(local->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+              cudaGetLastError();
+              v.ok = false;
+              continue;
+            }
+            cudaGetLastError();
+          }
+          v.p[b] = (void*)(uintptr_t)rec.raw[b];
+        } else {
+          void* ptr = nullptr;
+          for (const IpcMapping& m : s.mapped)
+            if (memcmp(&m.handle, &rec.handle[b], sizeof(cudaIpcMemHandle_t)) == 0) ptr = m.ptr;
+          if (!ptr) {
+            if (cudaIpcOpenMemHandle(&ptr, rec.handle[b], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+              cudaGetLastError();
+              v.ok = false;
+              continue;
+            }
+            IpcMapping m;
+            m.handle = rec.handle[b];
+            m.ptr = ptr;
+            s.mapped.push_back(m);
+          }
+          v.p[b] = ptr;
+        }
+        v.cap[b] = (size_t)rec.cap[b];
+      }
+      v.epoch = rec.epoch;
+      if (!v.ok) ok_local = 0;
+    }
+  }
+  // every rank must take the same path afterwards: peer-to-peer only if every shard could map every buffer
+  std::vector<u32*> okp(L);
+  for (size_t l = 0; l < L; ++l) {
+    Shard& s = cm->sh[l];
+    CM_CU(cm, cudaSetDevice(s.device));
+    SH_ENSURE(cm, s, s.small, 64);
+    *(u32*)s.h_pin = ok_local ? 0u : 1u;  // summed: 0 = nobody failed
+    CM_CU(cm, cudaMemcpyAsync(s.small.p, s.h_pin, 4, cudaMemcpyHostToDevice, s.ctx->stream));
+    okp[l] = s.small.as<u32>();
+  }
+  TRY(coll_allreduce_sum_u32(cm, okp, 1));
+  {
+    Shard& s = cm->sh[0];
+    CM_CU(cm, cudaSetDevice(s.device));
+    CM_CU(cm, cudaMemcpyAsync(s.h_pin, s.small.p, 4, cudaMemcpyDeviceToHost, s.ctx->stream));
+    TRY(sync_all(cm));
+    if (*(u32*)s.h_pin != 0) cm->p2p = false;  // for good: the exchange and the gather stay on NCCL
+  }
+  return IFTWT_OK;
+}
+
 }  // namespace
 
 // =================================================================================================
+// gather_root >= 0: the caller is iftwt_sharded_segment — when the root's gathered-row buffers are addressable
+// and large enough, the export kernels write the rows straight into them (export and gather fused).
 static int sharded_knn_normals_impl(iftwt_comm* cm, const iftwt_shard_in* in, int k, int want_normals,
-                                    double halo_radius, iftwt_shard_out* out) {
+                                    double halo_radius, iftwt_shard_out* out, int gather_root) {
   const int W = cm->nranks;
   const size_t L = cm->sh.size();
   if (!in || !out) return comm_fail(cm, IFTWT_ERR_INVALID, "null shard descriptors");
@@ -732,7 +916,7 @@ static int sharded_knn_normals_impl(iftwt_comm* cm, const iftwt_shard_in* in, in
     cudaEventRecord(s.ev[0], c->stream);
     const u32 n = (u32)in[l].n;
     const float4* pts = (const float4*)in[l].d_points;
-    SH_LAUNCH(s, shard_meta_init_kernel, 1, 32, (ShardMeta*)s.meta.p, n, (u32)in[l].gid0);
+    SH_LAUNCH(s, shard_meta_init_kernel, 1, 32, (ShardMeta*)s.meta.p, n, (u32)in[l].gid0, s.epoch);
     if (n) SH_LAUNCH(s, shard_bbox_kernel, c->sm_count * 8, 256, pts, n, (ShardMeta*)s.meta.p);
     if (estimate && n) {
       // the slice as the ctx's cloud, SHARD_SAMPLE of its points as external queries (general k-NN path)
@@ -787,6 +971,13 @@ static int sharded_knn_normals_impl(iftwt_comm* cm, const iftwt_shard_in* in, in
   }
   if (bad) return comm_fail(cm, IFTWT_ERR_NONFINITE, "the cloud holds %llu non-finite points", (unsigned long long)bad);
   if (n_total == 0) return comm_fail(cm, IFTWT_ERR_INVALID, "empty cloud");
+  {  // some rank (re)allocated a peer-writable buffer since the views were made: every rank sees it here
+    static const bool p2p_env = !(getenv("IFTWT_SHARD_P2P") && atoi(getenv("IFTWT_SHARD_P2P")) == 0);
+    if (!p2p_env) cm->p2p = false;
+    bool stale = false;
+    for (int r = 0; r < W; ++r) stale = stale || cm->sh[0].view[r].epoch != metas[r].epoch;
+    if (cm->p2p && stale) TRY(peers_refresh(cm));
+  }
   if (n_total > (uint64_t)GID_MASK) return comm_fail(cm, IFTWT_ERR_UNSUPPORTED, "more than 2^31 - 1 points");
   double ext = fmax(fmax(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
   if (!(ext > 0.0)) ext = 1.0;
@@ -799,6 +990,7 @@ static int sharded_knn_normals_impl(iftwt_comm* cm, const iftwt_shard_in* in, in
 
   int attempts = 0;
   float kth_max = 0.f;
+  bool p2p_last_x = false, p2p_call_ok = true;
   while (true) {
     ++attempts;
     if (attempts > 40) return comm_fail(cm, IFTWT_ERR_CUDA, "sharded k-NN: halo radius did not converge");
@@ -892,6 +1084,22 @@ static int sharded_knn_normals_impl(iftwt_comm* cm, const iftwt_shard_in* in, in
       }
     // ---- phase D: the exchange ----
     std::vector<std::vector<size_t>> send_off(L, std::vector<size_t>(W)), recv_off(L, std::vector<size_t>(W));
+    std::vector<size_t> need(W, 0), owned_of(W, 0);   // points rank d receives / owns
+    for (int d = 0; d < W; ++d)
+      for (int r = 0; r < W; ++r) {
+        need[d] += M[(size_t)r * W + d];
+        owned_of[d] += MO[(size_t)r * W + d];
+      }
+    // peer to peer iff every rank's receive buffers are mapped everywhere and large enough — decided on
+    // numbers every rank holds identically (the counts matrix, the capacities published at the last refresh)
+    // (an attempt that had to fall back to NCCL grows receive buffers, i.e. moves pointers the views of this call
+    // do not know yet: the rest of the call stays on NCCL)
+    bool p2p_x = cm->p2p && p2p_call_ok;
+    for (int d = 0; d < W && p2p_x; ++d) {
+      const PeerView& v = cm->sh[0].view[d];
+      p2p_x = v.ok && v.epoch == metas[d].epoch && v.p[PB_RX_PTS] && v.p[PB_RX_GID] &&
+              (need[d] + 1) * 16 <= v.cap[PB_RX_PTS] && (need[d] + 1) * 4 <= v.cap[PB_RX_GID];
+    }
     A2APayload pp, pg;
     pp.elem = 16;
     pg.elem = 4;
@@ -899,35 +1107,71 @@ static int sharded_knn_normals_impl(iftwt_comm* cm, const iftwt_shard_in* in, in
     for (size_t l = 0; l < L; ++l) {
       Shard& s = cm->sh[l];
       CM_CU(cm, cudaSetDevice(s.device));
-      size_t so = 0, ro = 0, owned = 0, sent_halo = 0;
+      size_t so = 0, ro = 0, sent_halo = 0;
       for (int r = 0; r < W; ++r) {
         send_off[l][r] = so;
         recv_off[l][r] = ro;
         so += M[(size_t)s.rank * W + r];
         ro += M[(size_t)r * W + s.rank];
-        owned += MO[(size_t)r * W + s.rank];
         if (r != s.rank) sent_halo += M[(size_t)s.rank * W + r] - MO[(size_t)s.rank * W + r];
       }
       s.m_total = ro;
-      s.n_owned = owned;
+      s.n_owned = owned_of[s.rank];
       s.out.halo_bytes_sent = (uint64_t)sent_halo * 20u;
       s.out.exchange_bytes_sent = (uint64_t)(so - M[(size_t)s.rank * W + s.rank]) * 20u;
       if (ro >= 0x7FFFFFF0ull) return comm_fail(cm, IFTWT_ERR_UNSUPPORTED, "a shard would hold 2^31 points");
-      SH_ENSURE(cm, s, s.send_pts, (so + 1) * 16);
-      SH_ENSURE(cm, s, s.send_gid, (so + 1) * 4);
-      SH_ENSURE(cm, s, s.ctx->pts_in, (ro + 1) * 16);  // received straight into the ctx's cloud buffer
-      SH_ENSURE(cm, s, s.recv_gid, (ro + 1) * 4);
+      PackDst dst;
+      memset(&dst, 0, sizeof dst);
+      if (p2p_x) {
+        for (int d = 0; d < W; ++d) {
+          dst.pts[d] = (float4*)s.view[d].p[PB_RX_PTS];
+          dst.gid[d] = (u32*)s.view[d].p[PB_RX_GID];
+          size_t base = 0;  // where this source's block starts in d's receive buffer
+          for (int r = 0; r < s.rank; ++r) base += M[(size_t)r * W + d];
+          dst.base[d] = (u32)base;
+        }
+      } else {
+        TRY(peer_ensure(cm, s, PB_RX_PTS, (ro + 1) * 16));
+        TRY(peer_ensure(cm, s, PB_RX_GID, (ro + 1) * 4));
+        SH_ENSURE(cm, s, s.send_pts, (so + 1) * 16);
+        SH_ENSURE(cm, s, s.send_gid, (so + 1) * 4);
+        for (int d = 0; d < W; ++d) {
+          dst.pts[d] = s.send_pts.as<float4>();
+          dst.gid[d] = s.send_gid.as<u32>();
+          dst.base[d] = (u32)send_off[l][d];
+        }
+      }
       const u32 n = (u32)in[l].n;
       if (n)
         SH_LAUNCH(s, shard_pack_kernel, nblk[l], 256, (const float4*)in[l].d_points, n, (u32)in[l].gid0,
-                  (const u32*)s.route.as<u32>(), (const u32*)s.blk_off.as<u32>(), nblk[l], W, s.send_pts.as<float4>(),
-                  s.send_gid.as<u32>());
+                  (const u32*)s.route.as<u32>(), (const u32*)s.blk_off.as<u32>(), nblk[l], W, dst);
       cudaEventRecord(s.ev[2], s.ctx->stream);
-      pp.send[l] = s.send_pts.p; pp.recv[l] = s.ctx->pts_in.p;
-      pg.send[l] = s.send_gid.p; pg.recv[l] = s.recv_gid.p;
+      pp.send[l] = s.send_pts.p; pp.recv[l] = s.pb[PB_RX_PTS].p;
+      pg.send[l] = s.send_gid.p; pg.recv[l] = s.pb[PB_RX_GID].p;
+      sendp[l] = s.cnt.p;  // the barrier of the peer-to-peer path: 4 bytes from everybody
+      recvp[l] = s.cnt_all.p;
     }
-    TRY(coll_alltoallv(cm, {pp, pg}, M, send_off, recv_off));
+    p2p_last_x = p2p_x;
+    if (!p2p_x) p2p_call_ok = false;
+    if (p2p_x) {
+      // every pack kernel has written into its peers; a rank may read its receive buffer once all of them are
+      // done: a 4-byte all-gather, stream-ordered behind the pack kernel on every rank
+      TRY(coll_allgather(cm, sendp, recvp, 4));
+    } else {
+      TRY(coll_alltoallv(cm, {pp, pg}, M, send_off, recv_off));
+    }
     if (cm->loopback) TRY(sync_all(cm));
+    // the rows go straight into the root's gathered-row buffers (iftwt_sharded_segment) when those are mapped
+    // everywhere and hold the whole cloud: export and gather are one kernel then, 164 B per point over NVLink
+    // while the export runs instead of a second pass through NCCL
+    bool p2p_g = gather_root >= 0 && cm->p2p && want_normals;
+    if (p2p_g) {
+      const PeerView& v = cm->sh[0].view[gather_root];
+      p2p_g = v.ok && v.epoch == metas[gather_root].epoch && v.p[PB_G_GID] && v.p[PB_G_PTS] && v.p[PB_G_KNN] &&
+              v.p[PB_G_D2] && v.p[PB_G_NRM] && (n_total + 1) * 4 <= v.cap[PB_G_GID] &&
+              (n_total + 1) * 16 <= v.cap[PB_G_PTS] && (n_total * k + 1) * 4 <= v.cap[PB_G_KNN] &&
+              (n_total * k + 1) * 4 <= v.cap[PB_G_D2] && (n_total + 1) * 16 <= v.cap[PB_G_NRM];
+    }
     // ---- phase E: the single-GPU kernels on owned + halo points ----
     std::vector<u32*> violp(L);
     for (size_t l = 0; l < L; ++l) {
@@ -936,6 +1180,9 @@ static int sharded_knn_normals_impl(iftwt_comm* cm, const iftwt_shard_in* in, in
       iftwt_ctx* c = s.ctx;
       cudaEventRecord(s.ev[3], c->stream);
       const size_t m = s.m_total;
+      SH_ENSURE(cm, s, c->pts_in, (m + 1) * 16);
+      if (m)  // the receive buffer stays what peers write into; the ctx works on its own copy (0.06 ms per 12.5 M points)
+        CM_CU(cm, cudaMemcpyAsync(c->pts_in.p, s.pb[PB_RX_PTS].p, m * 16, cudaMemcpyDeviceToDevice, c->stream));
       ctx_adopt_cloud(c, m);
       if (m) {
         CM_CTX(cm, s, knn_run(c, k));
@@ -946,44 +1193,64 @@ static int sharded_knn_normals_impl(iftwt_comm* cm, const iftwt_shard_in* in, in
       const size_t no = s.n_owned;
       SH_ENSURE(cm, s, s.small, 64);
       CM_CU(cm, cudaMemsetAsync(s.small.p, 0, 64, c->stream));
-      SH_ENSURE(cm, s, s.o_gid, (no + 1) * 4);
-      SH_ENSURE(cm, s, s.o_pts, (no + 1) * 16);
-      SH_ENSURE(cm, s, s.o_knn, (no * k + 1) * 4);
-      SH_ENSURE(cm, s, s.o_d2, (no * k + 1) * 4);
-      if (want_normals) SH_ENSURE(cm, s, s.o_nrm, (no + 1) * 16);
+      u32* d_gid;
+      float4 *d_pts, *d_nrm;
+      int* d_knn;
+      float* d_d2;
+      s.exported_to_root = p2p_g;
+      if (p2p_g) {
+        size_t row_base = 0;  // rows arrive in rank order, as the NCCL gather would deliver them
+        for (int r = 0; r < s.rank; ++r) row_base += owned_of[r];
+        const PeerView& v = s.view[gather_root];
+        d_gid = (u32*)v.p[PB_G_GID] + row_base;
+        d_pts = (float4*)v.p[PB_G_PTS] + row_base;
+        d_nrm = (float4*)v.p[PB_G_NRM] + row_base;
+        d_knn = (int*)v.p[PB_G_KNN] + row_base * k;
+        d_d2 = (float*)v.p[PB_G_D2] + row_base * k;
+      } else {
+        SH_ENSURE(cm, s, s.o_gid, (no + 1) * 4);
+        SH_ENSURE(cm, s, s.o_pts, (no + 1) * 16);
+        SH_ENSURE(cm, s, s.o_knn, (no * k + 1) * 4);
+        SH_ENSURE(cm, s, s.o_d2, (no * k + 1) * 4);
+        if (want_normals) SH_ENSURE(cm, s, s.o_nrm, (no + 1) * 16);
+        d_gid = s.o_gid.as<u32>();
+        d_pts = s.o_pts.as<float4>();
+        d_nrm = want_normals ? s.o_nrm.as<float4>() : nullptr;
+        d_knn = s.o_knn.as<int>();
+        d_d2 = s.o_d2.as<float>();
+      }
       if (m && no) {
         SH_ENSURE(cm, s, s.flag, (m + 1) * 4);
         SH_ENSURE(cm, s, s.pos, (m + 1) * 4);
         SH_ENSURE(cm, s, s.owned_idx, (no + 1) * 4);
-        SH_LAUNCH(s, shard_owned_flag_kernel, div_up(m, 256), 256, (const u32*)s.recv_gid.as<u32>(), (u32)m,
+        SH_LAUNCH(s, shard_owned_flag_kernel, div_up(m, 256), 256, (const u32*)s.pb[PB_RX_GID].p, (u32)m,
                   s.flag.as<u32>());
         size_t tb = 0;
         CM_CU(cm, cub::DeviceScan::ExclusiveSum(nullptr, tb, s.flag.as<u32>(), s.pos.as<u32>(), (int)m, c->stream));
         SH_ENSURE(cm, s, c->tmp, tb);
         CM_CU(cm, cub::DeviceScan::ExclusiveSum(c->tmp.p, tb, s.flag.as<u32>(), s.pos.as<u32>(), (int)m, c->stream));
         c->stats.kernel_launches += 2;
-        SH_LAUNCH(s, shard_owned_list_kernel, div_up(m, 256), 256, (const u32*)s.recv_gid.as<u32>(),
+        SH_LAUNCH(s, shard_owned_list_kernel, div_up(m, 256), 256, (const u32*)s.pb[PB_RX_GID].p,
                   (const u32*)s.pos.as<u32>(), (u32)m, s.owned_idx.as<u32>());
         const double lim = s_rad * (1.0 - 1e-6);
         const float s2_limit = (float)fmin(lim * lim, 3.0e38);
         // a shard that holds the whole cloud has exact rows whatever the radius
         const int have_all = (uint64_t)m == n_total ? 1 : 0;
         SH_LAUNCH(s, shard_export_points_kernel, div_up(no, 256), 256, (const u32*)s.owned_idx.as<u32>(), (u32)no,
-                  (const u32*)s.recv_gid.as<u32>(), (const float4*)c->pts_in.as<float4>(), (const u32*)c->inv.as<u32>(),
+                  (const u32*)s.pb[PB_RX_GID].p, (const float4*)c->pts_in.as<float4>(), (const u32*)c->inv.as<u32>(),
                   (const float4*)(want_normals ? c->nrm.as<float4>() : nullptr), (const u64*)c->kth.as<u64>(),
-                  s2_limit, have_all, s.o_gid.as<u32>(), s.o_pts.as<float4>(),
-                  want_normals ? s.o_nrm.as<float4>() : (float4*)nullptr, s.small.as<u32>());
+                  s2_limit, have_all, d_gid, d_pts, d_nrm, s.small.as<u32>());
         u32* gid_sorted = s.flag.as<u32>();  // the flags are consumed: their buffer is reused
-        SH_LAUNCH(s, shard_gid_sorted_kernel, div_up(m, 256), 256, (const u32*)s.recv_gid.as<u32>(),
+        SH_LAUNCH(s, shard_gid_sorted_kernel, div_up(m, 256), 256, (const u32*)s.pb[PB_RX_GID].p,
                   (const u32*)c->perm.as<u32>(), (u32)m, gid_sorted);
         if (k % 4 == 0)
           SH_LAUNCH(s, shard_export_rows4_kernel, div_up(no * (k / 4), 256), 256, (const u32*)s.owned_idx.as<u32>(),
                     (u32)no, k / 4, (const u32*)gid_sorted, (const u32*)c->inv.as<u32>(), (const uint4*)c->nbr.as<uint4>(),
-                    (const float4*)c->nd2.as<float4>(), s.o_knn.as<int4>(), s.o_d2.as<float4>());
+                    (const float4*)c->nd2.as<float4>(), (int4*)d_knn, (float4*)d_d2);
         else
           SH_LAUNCH(s, shard_export_rows_kernel, div_up(no * k, 256), 256, (const u32*)s.owned_idx.as<u32>(), (u32)no, k,
                     (const u32*)gid_sorted, (const u32*)c->inv.as<u32>(), (const u32*)c->nbr.as<u32>(),
-                    (const float*)c->nd2.as<float>(), s.o_knn.as<int>(), s.o_d2.as<float>());
+                    (const float*)c->nd2.as<float>(), d_knn, d_d2);
       }
       CM_CU(cm, cudaGetLastError());
       cudaEventRecord(s.ev[5], c->stream);
@@ -1020,11 +1287,13 @@ static int sharded_knn_normals_impl(iftwt_comm* cm, const iftwt_shard_in* in, in
     o.n_halo = s.m_total - s.n_owned;
     o.n_total = n_total;
     o.k = k;
-    o.d_gid = s.o_gid.as<uint32_t>();
-    o.d_points = s.o_pts.as<float>();
-    o.d_knn = s.o_knn.as<int32_t>();
-    o.d_d2 = s.o_d2.as<float>();
-    o.d_normals = want_normals ? s.o_nrm.as<float>() : nullptr;
+    // (rows that went straight to the root of iftwt_sharded_segment are not kept here)
+    o.d_gid = s.exported_to_root ? nullptr : s.o_gid.as<uint32_t>();
+    o.d_points = s.exported_to_root ? nullptr : s.o_pts.as<float>();
+    o.d_knn = s.exported_to_root ? nullptr : s.o_knn.as<int32_t>();
+    o.d_d2 = s.exported_to_root ? nullptr : s.o_d2.as<float>();
+    o.d_normals = (want_normals && !s.exported_to_root) ? s.o_nrm.as<float>() : nullptr;
+    o.peer_to_peer = (p2p_last_x ? 1 : 0) | (s.exported_to_root ? 2 : 0);
     o.halo_radius = s_rad;
     o.kth_distance_max = sqrt((double)kth_max);
     o.attempts = attempts;
@@ -1087,17 +1356,18 @@ static int gather_to_root(iftwt_comm* cm, int root, int k) {
         recv_off[l][r] = ro;
         ro += owned[r];
       }
-      SH_ENSURE(cm, s, s.g_gid, (n_total + 1) * 4);
-      SH_ENSURE(cm, s, s.g_pts, (n_total + 1) * 16);
-      SH_ENSURE(cm, s, s.g_knn, (n_total * k + 1) * 4);
-      SH_ENSURE(cm, s, s.g_d2, (n_total * k + 1) * 4);
-      SH_ENSURE(cm, s, s.g_nrm, (n_total + 1) * 16);
+      // peer-writable: the next call's export kernels write here directly (the epoch moves, the peers re-map)
+      TRY(peer_ensure(cm, s, PB_G_GID, (n_total + 1) * 4));
+      TRY(peer_ensure(cm, s, PB_G_PTS, (n_total + 1) * 16));
+      TRY(peer_ensure(cm, s, PB_G_KNN, (n_total * k + 1) * 4));
+      TRY(peer_ensure(cm, s, PB_G_D2, (n_total * k + 1) * 4));
+      TRY(peer_ensure(cm, s, PB_G_NRM, (n_total + 1) * 16));
     }
-    pg.send[l] = s.o_gid.p; pg.recv[l] = s.g_gid.p;
-    pp.send[l] = s.o_pts.p; pp.recv[l] = s.g_pts.p;
-    pk.send[l] = s.o_knn.p; pk.recv[l] = s.g_knn.p;
-    pd.send[l] = s.o_d2.p;  pd.recv[l] = s.g_d2.p;
-    pn.send[l] = s.o_nrm.p; pn.recv[l] = s.g_nrm.p;
+    pg.send[l] = s.o_gid.p; pg.recv[l] = s.pb[PB_G_GID].p;
+    pp.send[l] = s.o_pts.p; pp.recv[l] = s.pb[PB_G_PTS].p;
+    pk.send[l] = s.o_knn.p; pk.recv[l] = s.pb[PB_G_KNN].p;
+    pd.send[l] = s.o_d2.p;  pd.recv[l] = s.pb[PB_G_D2].p;
+    pn.send[l] = s.o_nrm.p; pn.recv[l] = s.pb[PB_G_NRM].p;
   }
   TRY(coll_alltoallv(cm, {pg, pp, pk, pd, pn}, M, send_off, recv_off));
   if (cm->loopback) TRY(sync_all(cm));
@@ -1207,7 +1477,7 @@ iftwt_ctx* iftwt_comm_ctx(iftwt_comm* cm, int local_index) {
 int iftwt_sharded_knn_normals(iftwt_comm* cm, const iftwt_shard_in* in, int k, int want_normals, double halo_radius,
                               iftwt_shard_out* out) {
   if (!cm) return comm_fail(nullptr, IFTWT_ERR_INVALID, "null comm");
-  return sharded_knn_normals_impl(cm, in, k, want_normals, halo_radius, out);
+  return sharded_knn_normals_impl(cm, in, k, want_normals, halo_radius, out, -1);
 }
 
 int iftwt_sharded_segment(iftwt_comm* cm, const iftwt_shard_in* in, const iftwt_segment_params* p, double halo_radius,
@@ -1221,8 +1491,8 @@ int iftwt_sharded_segment(iftwt_comm* cm, const iftwt_shard_in* in, const iftwt_
                      "the sharded pipeline shares one neighbourhood size between graph, normals and region growing "
                      "(and needs the curvature gate inactive, threshold >= 0.34)");
   const int k = p->k_graph;
-  TRY(sharded_knn_normals_impl(cm, in, k, 1, halo_radius, out));
-  TRY(gather_to_root(cm, root, k));
+  TRY(sharded_knn_normals_impl(cm, in, k, 1, halo_radius, out, root));
+  if (!cm->sh[0].exported_to_root) TRY(gather_to_root(cm, root, k));  // else: the export kernels wrote them there
   for (Shard& s : cm->sh) {
     if (s.rank != root) continue;
     CM_CU(cm, cudaSetDevice(s.device));
@@ -1231,8 +1501,8 @@ int iftwt_sharded_segment(iftwt_comm* cm, const iftwt_shard_in* in, const iftwt_
     // the cloud in global-id order + where each gathered row sits
     SH_ENSURE(cm, s, s.g_pos, (n + 1) * 4);
     SH_ENSURE(cm, s, c->pts_in, (n + 1) * 16);
-    SH_LAUNCH(s, shard_pos_of_gid_kernel, div_up(n, 256), 256, (const u32*)s.g_gid.as<u32>(), (u32)n, s.g_pos.as<u32>(),
-              (const float4*)s.g_pts.as<float4>(), c->pts_in.as<float4>());
+    SH_LAUNCH(s, shard_pos_of_gid_kernel, div_up(n, 256), 256, (const u32*)s.pb[PB_G_GID].p, (u32)n, s.g_pos.as<u32>(),
+              (const float4*)s.pb[PB_G_PTS].p, c->pts_in.as<float4>());
     ctx_adopt_cloud(c, n);
     CM_CTX(cm, s, grid_build(c, k));
     SH_ENSURE(cm, s, c->nbr, n * k * 4);
@@ -1241,7 +1511,7 @@ int iftwt_sharded_segment(iftwt_comm* cm, const iftwt_shard_in* in, const iftwt_
     SH_ENSURE(cm, s, c->fb_list, n * 8);
     SH_ENSURE(cm, s, c->nrm, n * 16);
     SH_LAUNCH(s, shard_install_kernel, div_up(n * 32, 256), 256, (const u32*)s.g_pos.as<u32>(),
-              (const int*)s.g_knn.as<int>(), (const float*)s.g_d2.as<float>(), (const float4*)s.g_nrm.as<float4>(),
+              (const int*)s.pb[PB_G_KNN].p, (const float*)s.pb[PB_G_D2].p, (const float4*)s.pb[PB_G_NRM].p,
               (const u32*)c->perm.as<u32>(), (const u32*)c->inv.as<u32>(), (u32)n, k, c->nbr.as<u32>(),
               c->nd2.as<float>(), c->kth.as<u64>(), c->nrm.as<float4>());
     CM_CU(cm, cudaGetLastError());

@@ -337,6 +337,11 @@ typedef struct iftwt_shard_out {
   float ms_compute;          /* grid + k-NN + normals on owned + halo points,                  */
   float ms_export;           /* rows to global ids + exactness check                           */
   float knn_cell_ms;         /* the k-NN fast-path kernel inside ms_compute                    */
+  int peer_to_peer;          /* bit 0: the exchange was written by the pack kernel straight into the peers' receive
+                                buffers over NVLink (cudaIpc / peer access) instead of ncclSend / ncclRecv; bit 1:
+                                the rows went straight into the root's buffers (iftwt_sharded_segment) — the d_*
+                                pointers above are NULL then.  Both need one earlier call on the comm (the first
+                                one sizes the buffers and runs over NCCL); IFTWT_SHARD_P2P=0 keeps everything on NCCL */
 } iftwt_shard_out;
 
 /* `in` / `out`: one entry per LOCAL shard (1 in the process-per-GPU mode).  halo_radius <= 0: estimated

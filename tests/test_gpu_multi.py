@@ -64,7 +64,9 @@ def test_sharded_two_gpus_nccl_single_process():
         torch.cuda.synchronize(r)
     with api.Comm.all([0, 1]) as cm:
         sl = [(t.data_ptr(), t.shape[0], lo) for t, (lo, hi) in zip(slabs, bounds)]
-        outs = cm.sharded_knn_normals(sl, k, True, 0.0)
+        cm.sharded_knn_normals(sl, k, True, 0.0)          # sizes the receive buffers, NCCL exchange
+        outs = cm.sharded_knn_normals(sl, k, True, 0.0)   # pack kernel writes into the peer GPU over NVLink
+        assert all(o.peer_to_peer == 1 for o in outs)
         seen = np.zeros(n, np.int32)
         for r, o in enumerate(outs):
             v = {name: t.cpu().numpy() for name, t in sharded.as_torch(o, r).items()}
@@ -74,8 +76,10 @@ def test_sharded_two_gpus_nccl_single_process():
             assert np.array_equal(v["normals"].view(np.uint32), rn[gid].view(np.uint32))
             assert o.halo_bytes_sent > 0 and o.attempts == 1
         assert np.all(seen == 1)
-        cost, label, ns, _ = cm.sharded_segment(sl, k, rg, root=1, n_total=n)
-        assert ns == rns and np.array_equal(cost, rcost) and np.array_equal(label, rlabel)
+        for call in range(2):   # the second call's export kernels write the rows into GPU 1 directly
+            cost, label, ns, so = cm.sharded_segment(sl, k, rg, root=1, n_total=n)
+            assert ns == rns and np.array_equal(cost, rcost) and np.array_equal(label, rlabel), call
+        assert all(o.peer_to_peer == 3 for o in so)
 
 
 def test_bench_cfg4_two_gpus():
@@ -90,6 +94,7 @@ def test_bench_cfg4_two_gpus():
     assert sum(d["owned_per_rank"]) == 4000000 and min(d["owned_per_rank"]) > 1200000
     assert 0 < sum(d["halo_per_rank"]) < 800000 and d["halo_bytes_over_nvlink"] > 0
     assert r["detail"]["seeds"] > 0 and r["e2e"]["value"] > 0
+    assert d["peer_to_peer"] == 1 and r["detail"]["segment_peer_to_peer"] == 3   # cudaIpc between the two processes
 
 
 def test_bench_two_gpus_default_line_carries_the_sharded_pass():

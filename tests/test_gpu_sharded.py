@@ -38,14 +38,28 @@ def _run_sharded(pts, k, world, radius=0.0, bounds=None):
     bounds = bounds or [sharded.slice_bounds(n, world, r) for r in range(world)]
     slabs = [torch.from_numpy(np.ascontiguousarray(pts[lo:hi])).to(dev) for lo, hi in bounds]
     torch.cuda.synchronize()
-    res = []
-    with api.Comm.all([0] * world) as cm:
-        assert cm.info() == {"nranks": world, "n_local": world, "first_local_rank": 0}
-        outs = cm.sharded_knn_normals([(t.data_ptr() if t.numel() else 0, t.shape[0], lo)
-                                       for t, (lo, hi) in zip(slabs, bounds)], k, True, radius)
+    def collect(outs):
+        res = []
         for o in outs:
             v = sharded.as_torch(o, 0)
             res.append({name: (None if t is None else t.cpu().numpy()) for name, t in v.items()} | {"o": o.as_dict()})
+        return res
+
+    with api.Comm.all([0] * world) as cm:
+        assert cm.info() == {"nranks": world, "n_local": world, "first_local_rank": 0}
+        sl = [(t.data_ptr() if t.numel() else 0, t.shape[0], lo) for t, (lo, hi) in zip(slabs, bounds)]
+        # the first call on a comm sizes the receive buffers and moves the points with copies (NCCL between GPUs);
+        # from the second call on the pack kernel writes straight into the peers' receive buffers.  Same rows.
+        first = collect(cm.sharded_knn_normals(sl, k, True, radius))
+        assert all(r["o"]["peer_to_peer"] == 0 for r in first)
+        res = collect(cm.sharded_knn_normals(sl, k, True, radius))
+        for a, b in zip(first, res):
+            assert a["o"]["n_owned"] == b["o"]["n_owned"] and a["o"]["n_halo"] == b["o"]["n_halo"]
+            for name in ("gid", "points", "knn", "d2", "normals"):
+                if a[name] is not None:
+                    assert np.array_equal(a[name].view(np.uint32), b[name].view(np.uint32)), name
+            if b["o"]["attempts"] == 1:
+                assert b["o"]["peer_to_peer"] == 1
     return res
 
 
@@ -226,10 +240,15 @@ def test_sharded_segment_equals_single_gpu_segment(world, gradient):
     torch.cuda.synchronize()
     root = world - 1
     with api.Comm.all([0] * world) as cm:
-        cost, label, ns, outs = cm.sharded_segment([(t.data_ptr(), t.shape[0], lo) for t, (lo, hi) in zip(slabs, bounds)],
-                                                   k, rg, root=root, n_total=n, gradient_weights=gradient)
-        assert ns == rns
-        assert np.array_equal(cost, rcost) and np.array_equal(label, rlabel)
+        sl = [(t.data_ptr(), t.shape[0], lo) for t, (lo, hi) in zip(slabs, bounds)]
+        for call in range(3):
+            # call 0: exchange and gather by copies (they size the receive buffers and the root's buffers); from
+            # call 1 on the pack kernel writes into the peers' receive buffers and the export kernels write the rows
+            # straight into the root's buffers
+            cost, label, ns, outs = cm.sharded_segment(sl, k, rg, root=root, n_total=n, gradient_weights=gradient)
+            assert ns == rns, call
+            assert np.array_equal(cost, rcost) and np.array_equal(label, rlabel), call
+            assert all(o.peer_to_peer == (0, 3, 3)[call] for o in outs), (call, [o.peer_to_peer for o in outs])
         # the root's ctx now holds the whole cloud and its graph: the follow-up calls of the ABI apply
         rctx = cm.ctx(root)
         rctx.n = n
