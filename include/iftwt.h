@@ -281,7 +281,10 @@ IFTWT_API int iftwt_batch_segment(iftwt_batch* batch, const void* const* clouds,
  * (the points of the 26 coarse cells around each of its own) from its peers over NVLink (grouped
  * ncclSend / ncclRecv), runs the single-GPU kernels, and keeps the rows of the points it owns,
  * translated to GLOBAL point ids.  The rows are bit-identical to what one GPU computes on the
- * whole cloud (ties break by global id).  The IFT does not shard: iftwt_sharded_segment gathers
+ * whole cloud (ties break by global id).  From a comm's second call on the exchange is written by
+ * the partition kernel straight into the peers' receive buffers (cudaIpc / peer access over NVLink)
+ * and the rows of iftwt_sharded_segment straight into the root's buffers; NCCL then only carries
+ * the small all-gathers / all-reduces that double as barriers.  The IFT does not shard: iftwt_sharded_segment gathers
  * the rows to one rank and runs graph / seeds / IFT there.  (csrc/shard.cu) */
 typedef struct iftwt_comm iftwt_comm;
 
