@@ -266,7 +266,9 @@ int grid_build(iftwt_ctx* c, int k) {
     // every sub-th point is enough: a cell holding m points shows a sampled point (m - 1) / sub
     // sampled companions on average, so m is estimated by 1 + sub * (run - 1).  (Sorting all
     // 10 M keys for this estimate cost 0.6 ms.)
-    const u32 sub = n >= (1u << 21) ? 8u : 1u;
+    // (clouds below 2 M points used to sort every key: a 2 M-point cloud of config 5 paid 0.15 ms for it; the
+    // sample stays above 2^18 points, four per sampled cell range at the coarsest level that matters)
+    const u32 sub = n >= (1u << 21) ? 8u : (n >= (1u << 19) ? n >> 18 : 1u);
     const u32 m = (n + sub - 1) / sub;
     LAUNCH(c, fine_key_kernel, div_up(m, 256), 256, 0, pts, m, sub, lo[0], lo[1], lo[2], 65536.0 / side, k0);
     CHECK_LAUNCH(c);
