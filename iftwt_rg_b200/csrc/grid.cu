@@ -304,13 +304,15 @@ int grid_build(iftwt_ctx* c, int k) {
       // neighbour lies outside the 3x3x3 block and the query leaves the fast path: 17.7 % of cfg5's queries,
       // 0.9 of its 2.0 ms of k-NN.  One level above the cell scale — where a cell holds enough sampled points
       // for the count to mean something — the ratio of the mean occupancy to its 25th percentile (both
-      // point-weighted) is 1.17 on the facade, 1.9 on the primitives scene, 1.7 on the statue.  At 1.35 or
-      // more the cell is sized for the sparse quarter instead: the occupancy target grows by that ratio
-      // (at most 2).  Swept on B200 (cfg5): beta 0.45 -> 5.35 ms per cloud, 0.7 -> 4.43, 0.85 -> 4.33,
+      // point-weighted), with the Poisson scatter of the sample taken out, is ~1.05 on the facade, ~1.8 on the
+      // primitives scene.  At 1.25 or more the cell is sized for the sparse quarter instead: the occupancy
+      // target grows by that ratio (at most 2).  Swept on B200 (cfg5): beta 0.45 -> 5.35 ms per cloud, 0.7 -> 4.43, 0.85 -> 4.33,
       // 1.0 -> 4.46; cfg3 keeps 0.45.  Any cell size gives the same, exact rows.
       int l = 0;
       while (l < 16 && ppc[l + 1] >= target) ++l;
-      const int L2 = l - 1;
+      int L2 = l - 1;
+      // sampled points per cell at that level: below 16 the 25th percentile is mostly Poisson noise — one level up
+      if (L2 > 1 && (ppc[L2] - 1.0) / (double)sub + 1.0 < 16.0) --L2;
       if (L2 >= 1 && ppc[L2] >= 8.0) {
         const u32* hh2 = (const u32*)c->h_hist + (size_t)L2 * OCC_BINS;
         unsigned long long tot = 0;
@@ -324,9 +326,12 @@ int grid_build(iftwt_ctx* c, int k) {
           }
           const double run25 = exp2(((double)b25 + 0.5) / (double)OCC_BINS_PER_OCTAVE);
           const double occ25 = fmax(1.0, 1.0 + (double)sub * (run25 - 1.0));
-          const double spread = ppc[L2] / occ25;
+          // a uniform cloud already shows mean / p25 = 1 / (1 - 0.674 / sqrt(lambda)) from the Poisson scatter of
+          // the lambda sampled points per cell: taken out, so that the ratio measures the cloud, not the sample
+          const double lambda = fmax(1.0, (ppc[L2] - 1.0) / (double)sub + 1.0);
+          const double spread = ppc[L2] / occ25 * fmax(0.5, 1.0 - 0.674 / sqrt(lambda));
           c->stats_density_spread = spread;
-          if (spread >= 1.35) {
+          if (spread >= 1.25) {
             beta *= fmin(spread, 2.0);
             target = beta * (double)(k < 2 ? 2 : k) + 1.0;
           }
