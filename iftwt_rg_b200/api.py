@@ -146,6 +146,7 @@ def load_library(build_if_missing: bool = True):
     lib.iftwt_comm_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     lib.iftwt_comm_ctx.argtypes = [vp, i32]
     lib.iftwt_comm_ctx.restype = vp
+    lib.iftwt_comm_upload.argtypes = [vp, i32, vp, sz, C.c_uint64, C.POINTER(ShardIn)]
     lib.iftwt_sharded_knn_normals.argtypes = [vp, C.POINTER(ShardIn), i32, i32, C.c_double, C.POINTER(ShardOut)]
     lib.iftwt_sharded_segment.argtypes = [vp, C.POINTER(ShardIn), C.POINTER(SegmentParams), C.c_double, i32, vp, vp,
                                           C.POINTER(sz), C.POINTER(ShardOut)]
@@ -544,6 +545,14 @@ class Comm:
         if not h:
             raise IftwtError(-1, "no such local shard")
         return Context(_borrowed=h)
+
+    def upload(self, local_index: int, pts: np.ndarray, gid0: int):
+        """Host slice -> a device buffer the comm owns; returns the (device_ptr, n, gid0) triple the calls below take."""
+        pts = np.ascontiguousarray(pts, np.float32)
+        assert pts.ndim == 2 and pts.shape[1] == 4
+        si = ShardIn()
+        self._check(self._lib.iftwt_comm_upload(self._h, local_index, _ptr(pts), pts.shape[0], gid0, C.byref(si)))
+        return (si.d_points or 0, si.n, si.gid0)
 
     def _ins(self, slices):
         """slices: one (device_ptr, n, gid0) per local shard."""

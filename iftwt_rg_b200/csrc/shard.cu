@@ -552,7 +552,7 @@ struct Shard {
   ncclComm_t nccl = nullptr;
   void* h_pin = nullptr;          // pinned scratch (4 KB)
   DevBuf meta, meta_all, hist, hist_scan, owner, route, blk, blk_off, send_pts, send_gid, cnt, cnt_all, flag, pos,
-      owned_idx, small, sample_q, sample_d2, sample_idx, peer_rec, peer_rec_all;
+      owned_idx, small, sample_q, sample_d2, sample_idx, peer_rec, peer_rec_all, in_pts;
   DevBuf o_gid, o_pts, o_knn, o_d2, o_nrm;             // results of iftwt_sharded_knn_normals
   DevBuf g_pos;                                        // root: where each gathered row sits
   PeerBuf pb[PB_COUNT];                                // rx_* : received points / ids; g_* : root's gathered rows
@@ -735,7 +735,7 @@ void shard_free(Shard& s) {
   cudaStreamSynchronize(s.ctx->stream);
   DevBuf* bufs[] = {&s.meta, &s.meta_all, &s.hist, &s.hist_scan, &s.owner, &s.route, &s.blk, &s.blk_off, &s.send_pts, &s.send_gid,
                     &s.cnt, &s.cnt_all, &s.flag, &s.pos, &s.owned_idx, &s.small, &s.sample_q, &s.sample_d2,
-                    &s.sample_idx, &s.peer_rec, &s.peer_rec_all, &s.o_gid, &s.o_pts, &s.o_knn, &s.o_d2, &s.o_nrm, &s.g_pos};
+                    &s.sample_idx, &s.peer_rec, &s.peer_rec_all, &s.in_pts, &s.o_gid, &s.o_pts, &s.o_knn, &s.o_d2, &s.o_nrm, &s.g_pos};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (IpcMapping& m : s.mapped) cudaIpcCloseMemHandle(m.ptr);
@@ -1472,6 +1472,22 @@ int iftwt_comm_info(const iftwt_comm* cm, int* nranks, int* n_local, int* first_
 iftwt_ctx* iftwt_comm_ctx(iftwt_comm* cm, int local_index) {
   if (!cm || local_index < 0 || (size_t)local_index >= cm->sh.size()) return nullptr;
   return cm->sh[local_index].ctx;
+}
+
+int iftwt_comm_upload(iftwt_comm* cm, int local_index, const void* host_points, size_t n, uint64_t gid0,
+                      iftwt_shard_in* in) {
+  if (!cm) return comm_fail(nullptr, IFTWT_ERR_INVALID, "null comm");
+  if (local_index < 0 || (size_t)local_index >= cm->sh.size() || !in || (n && !host_points))
+    return comm_fail(cm, IFTWT_ERR_INVALID, "bad upload (local shard %d of %zu)", local_index, cm->sh.size());
+  Shard& s = cm->sh[(size_t)local_index];
+  CM_CU(cm, cudaSetDevice(s.device));
+  SH_ENSURE(cm, s, s.in_pts, (n + 1) * 16);
+  if (n) CM_CU(cm, cudaMemcpyAsync(s.in_pts.p, host_points, n * 16, cudaMemcpyHostToDevice, s.ctx->stream));
+  CM_CU(cm, cudaStreamSynchronize(s.ctx->stream));
+  in->d_points = s.in_pts.p;
+  in->n = n;
+  in->gid0 = gid0;
+  return IFTWT_OK;
 }
 
 int iftwt_sharded_knn_normals(iftwt_comm* cm, const iftwt_shard_in* in, int k, int want_normals, double halo_radius,

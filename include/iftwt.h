@@ -316,6 +316,12 @@ typedef struct iftwt_shard_in {
   uint64_t gid0;
 } iftwt_shard_in;
 
+/* For hosts without CUDA of their own (the reference's main.cpp holds its cloud in a std::vector): copies
+ * `n` packed float4 {x,y,z,intensity} records from HOST memory into a device buffer the comm owns for local
+ * shard `local_index`, and fills *in for the calls below.  The buffer lives until the next upload to that shard. */
+IFTWT_API int iftwt_comm_upload(iftwt_comm* comm, int local_index, const void* host_points, size_t n, uint64_t gid0,
+                                iftwt_shard_in* in);
+
 /* Result of one shard.  Device pointers are owned by the comm and valid until its next call. */
 typedef struct iftwt_shard_out {
   size_t n_owned;            /* points of the Morton range this rank owns                      */

@@ -136,3 +136,23 @@ def test_ift_lakes_and_plateaus_are_schedule_independent(ctx):
     assert np.array_equal(runs[0][1], rlabel)
     assert orc.ift_audit(off, adj, w, seeds, runs[0][0], runs[0][1]) == 0
     assert (rcost < 500).mean() > 0.99
+
+
+def test_density_spread_sizes_the_cell_for_the_sparse_part():
+    """grid.cu: a uniformly sampled surface leaves the cell alone; a cloud whose ground plane is sampled at a
+    third of the density of its other parts gets a larger cell and (nearly) no query leaves the fast path.
+    Either way the rows are exact (every parity test runs through this code)."""
+    from iftwt_rg_b200 import api
+    with api.Context(0) as ctx:
+        fac = synth.scene_facade(600_000, seed=3)
+        ctx.set_cloud(fac)
+        ctx.knn(16, download=False)
+        s_fac = ctx.stats()
+        prim = synth.scene_primitives(600_000, seed=3)
+        ctx.set_cloud(prim)
+        idx, d2 = ctx.knn(16)
+        s_prim = ctx.stats()
+    assert 0.9 < s_fac["density_spread"] < 1.25 <= s_prim["density_spread"] < 2.5
+    assert s_prim["knn_fallback"] < 0.02 * len(prim)
+    ridx, rd2 = orc.knn_self(prim, 16)
+    assert np.array_equal(idx, ridx) and np.array_equal(d2, rd2)

@@ -109,6 +109,24 @@ def test_one_shard_is_the_single_gpu_path():
     assert res[0]["o"]["n_owned"] == len(pts) and res[0]["o"]["n_halo"] == 0 and res[0]["o"]["attempts"] == 1
 
 
+def test_host_slices_through_iftwt_comm_upload():
+    """A host without CUDA of its own hands over host memory (iftwt_comm_upload); rows fetched back with plain
+    cudaMemcpy-free means are out of this test's scope — the segmentation result is compared instead."""
+    from iftwt_rg_b200 import api, sharded
+    pts = synth.scene_facade(150_000, seed=0x33)
+    n, k = len(pts), 16
+    rg = api.RgParams(50, 10000, k, 0.1, 1.0)
+    with api.Context(0) as ctx:
+        ctx.set_cloud(pts)
+        rcost, rlabel, rns = ctx.segment(k, k, rg)
+    with api.Comm.all([0, 0, 0]) as cm:
+        sl = [cm.upload(r, pts[lo:hi], lo) for r, (lo, hi) in enumerate(sharded.slice_bounds(n, 3, r) for r in range(3))]
+        cost, label, ns, _ = cm.sharded_segment(sl, k, rg, root=0, n_total=n)
+        assert ns == rns and np.array_equal(cost, rcost) and np.array_equal(label, rlabel)
+        with pytest.raises(api.IftwtError):
+            cm.upload(3, pts[:10], 0)
+
+
 def test_owner_follows_the_partition_rule():
     """Numpy restatement of the rule (shard.cu phases B, C): coarse cells of side s over the global box,
     Morton key (x most significant), bins = the key's top <= 18 bits, bin b goes to rank
