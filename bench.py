@@ -99,8 +99,9 @@ def parse():
     ap.add_argument("--no-parity", action="store_true", help="skip detail.parity (GPU vs oracle on the cpu sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-inflight", type=int, default=3,
-                    help="clouds in flight in the e2e measurement (one ctx + stream each)")
+    ap.add_argument("--e2e-lanes", type=int, default=2,
+                    help="lanes of the e2e measurement (iftwt_batch_segment with host clouds; each lane has its own "
+                         "upload / download stream)")
     return ap.parse_args()
 
 
@@ -719,57 +720,46 @@ def main():
         for _ in range(2):
             step_e2e()
         ms_serial = timed(step_e2e, args.steps)
-        # pipelined: `inflight` ctxs (one stream each, independent by the ABI's contract), one host
-        # thread per ctx; the copies of one cloud overlap the kernels of the other.  Every step
-        # still uploads its cloud from pinned memory and downloads cost + label.
-        inflight = max(1, args.e2e_inflight)
+        # pipelined: iftwt_batch_segment with HOST clouds and host results — `e2e_lanes` ctxs, each with its own
+        # upload and download stream (csrc/capi.cu: LaneIO): the lane's next cloud is uploaded while the current
+        # one is segmented and the results are downloaded while the next one runs.  Every step still uploads
+        # its cloud from pinned memory and downloads cost + label.
+        e2e_lanes = max(1, args.e2e_lanes)
         ms_e2e = ms_serial
-        if inflight > 1:
-            dev = torch.device("cuda", local)
-            ctxs = [ctx] + [api.Context(local) for _ in range(inflight - 1)]
-            streams = [stream] + [torch.cuda.ExternalStream(c.stream(), device=dev) for c in ctxs[1:]]
-            outs = [(cost_np, label_np)]
-            keep = []
-            for _ in ctxs[1:]:
+        keep = []
+        with api.Batch(local, e2e_lanes) as bt:
+            nb = args.steps
+            n_out = min(nb, 2 * e2e_lanes + 2)      # result buffers are reused round-robin by the caller
+            for _ in range(n_out):
                 hc = torch.empty(n, dtype=torch.int32).pin_memory()
                 hl = torch.empty(n, dtype=torch.int32).pin_memory()
-                keep.append((hc, hl))
-                outs.append((hc.numpy().view(np.uint32), hl.numpy().view(np.uint32)))
-
-            def worker(i, steps):
-                for j in range(i, steps, inflight):
-                    ctxs[i].set_cloud(in_nps[j % per_rank])
-                    ctxs[i].segment(k, k, rg, cost=outs[i][0], label=outs[i][1])
-
-            def run_pipelined(steps):
-                ts = [threading.Thread(target=worker, args=(i, steps)) for i in range(inflight)]
-                for t in ts:
-                    t.start()
-                for t in ts:
-                    t.join()
-
-            run_pipelined(2 * inflight)
+                keep.append((hc.numpy().view(np.uint32), hl.numpy().view(np.uint32), hc, hl))
+            h_clouds = [in_nps[j % per_rank] for j in range(nb)]
+            costs = [keep[j % n_out][0] for j in range(nb)]
+            labels = [keep[j % n_out][1] for j in range(nb)]
+            w = max(2 * e2e_lanes, 3)
+            bt.segment(h_clouds[:w] if nb >= w else (h_clouds * w)[:w], k, rg, cost=(costs * w)[:w],
+                       label=(labels * w)[:w])
+            st0 = torch.cuda.ExternalStream(bt.ctx(0).stream(), device=torch.device("cuda", local))
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             barrier()
-            e0.record(stream)
-            run_pipelined(args.steps)
-            for st in streams[1:]:
-                ev = torch.cuda.Event()
-                ev.record(st)
-                stream.wait_event(ev)
-            e1.record(stream)
+            e0.record(st0)
+            bt.segment(h_clouds, k, rg, cost=costs, label=labels)   # returns when every copy has landed
+            e1.record(st0)
             barrier()
             ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
             if world > 1:
                 dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             ms_e2e = float(ms.item())
-            if per_rank == 1:  # the same cloud went through every ctx
-                assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
-            for c in ctxs[1:]:
-                c.close()
+            if per_rank == 1:  # the same cloud went through every lane: same result as the serial ctx
+                assert np.array_equal(costs[0], cost_np) and np.array_equal(labels[0], label_np)
+                assert np.array_equal(costs[-1], cost_np) and np.array_equal(labels[-1], label_np)
+        inflight = e2e_lanes
         e2e = {"value": world * n * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(n * 16),
                "d2h_bytes_per_step": int(n * 8), "ms_per_step": ms_e2e / args.steps,
+               "entry_point": f"iftwt_batch_segment, host clouds + host results, {inflight} lanes, copies in the "
+                              "lanes' own upload / download streams",
                "clouds_in_flight": inflight, "serial_ms_per_step": ms_serial / args.steps,
                "serial_value": world * n * args.steps / (ms_serial * 1e-3)}
 

@@ -1,6 +1,7 @@
 // capi.cu — the extern "C" boundary declared in include/iftwt.h.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -114,6 +115,26 @@ void ctx_invalidate(iftwt_ctx* c) {
   c->rag_valid = false;
 }
 
+// Small device -> host reads (counters, the level table) are written by a kernel straight into the
+// ctx's mapped pinned mirrors instead of going through cudaMemcpyAsync: a 4-byte copy queues on the same
+// copy engine as the 80 MB result download (or the 160 MB upload) of ANOTHER ctx and waits for it, which
+// stalls this ctx's host thread for up to a millisecond at every round trip when several clouds are in
+// flight.  IFTWT_FETCH=copy restores the copies (A/B measurements).
+__global__ void fetch_words_kernel(u32* __restrict__ dst, const u32* __restrict__ src, u32 nw) {
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+int host_fetch(iftwt_ctx* c, void* h_dst, const void* d_src, size_t bytes) {
+  static const bool by_copy = getenv("IFTWT_FETCH") && !strcmp(getenv("IFTWT_FETCH"), "copy");
+  if (by_copy || (bytes & 3))
+    CU_TRY(c, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  else {
+    const u32 nw = (u32)(bytes / 4);
+    LAUNCH(c, fetch_words_kernel, nw > 1024 ? 4 : 1, nw >= 256 ? 256 : 32, 0, (u32*)h_dst, (const u32*)d_src, nw);
+    CHECK_LAUNCH(c);
+  }
+  return IFTWT_OK;
+}
+
 extern "C" {
 
 int iftwt_version(void) { return IFTWT_VERSION; }
@@ -158,7 +179,8 @@ int iftwt_create(iftwt_ctx** out, int device) {
   c->sm_count = prop.multiProcessorCount;
   if (cudaSetDevice(device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaMallocHost(&c->h_scalars, 4096) != cudaSuccess || cudaMallocHost(&c->h_hist, 17 * 256 * 4) != cudaSuccess) {
+      cudaHostAlloc(&c->h_scalars, 4096, cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostAlloc(&c->h_hist, 17 * 256 * 4, cudaHostAllocMapped) != cudaSuccess) {
     g_err = std::string("ctx setup failed: ") + cudaGetErrorString(cudaGetLastError());
     delete c;
     return IFTWT_ERR_CUDA;
@@ -654,11 +676,62 @@ void* iftwt_stream(iftwt_ctx* c) { return c ? (void*)c->stream : nullptr; }
 // LANES — one ctx, one stream and one host thread each, independent by the ABI's contract — that pull
 // clouds from one queue: the latency-bound stretches of one cloud are filled by the kernels of the
 // others.  Results are those of iftwt_segment on each cloud by construction.
+// Host clouds: every lane owns an upload and a download stream next to its ctx's compute stream.  The
+// lane's NEXT cloud is copied into the second of two staging buffers while the current one is being
+// segmented, and the results leave through a result buffer of the lane's own while the next cloud is
+// already running — the copies never sit in front of a kernel in the compute stream, so two lanes keep
+// the SMs as busy as with resident clouds (three ctxs that copy in their own streams, as the bench
+// drove them before, pay for the third cloud's share of the caches: 16.4 ms per 10 M-point cloud
+// against 15.4 with two).
+struct LaneIO {
+  cudaStream_t up = nullptr, down = nullptr;
+  void* in[2] = {nullptr, nullptr};
+  size_t in_cap[2] = {0, 0};
+  void* res = nullptr;
+  size_t res_cap = 0;
+  cudaEvent_t up_done[2] = {nullptr, nullptr}, res_ready = nullptr, down_done = nullptr;
+  bool ready = false;
+};
 struct iftwt_batch {
   int device = 0;
   std::vector<iftwt_ctx*> lanes;
+  std::vector<LaneIO> io;
   std::string err;
 };
+
+static cudaError_t lane_io_setup(LaneIO& io) {
+  if (io.ready) return cudaSuccess;
+  cudaError_t e;
+  if ((e = cudaStreamCreateWithFlags(&io.up, cudaStreamNonBlocking)) != cudaSuccess) return e;
+  if ((e = cudaStreamCreateWithFlags(&io.down, cudaStreamNonBlocking)) != cudaSuccess) return e;
+  cudaEvent_t* evs[] = {&io.up_done[0], &io.up_done[1], &io.res_ready, &io.down_done};
+  for (cudaEvent_t* ev : evs)
+    if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+  io.ready = true;
+  return cudaSuccess;
+}
+static void lane_io_free(LaneIO& io) {
+  if (io.up) cudaStreamSynchronize(io.up);
+  if (io.down) cudaStreamSynchronize(io.down);
+  for (int s = 0; s < 2; ++s)
+    if (io.in[s]) cudaFree(io.in[s]);
+  if (io.res) cudaFree(io.res);
+  cudaEvent_t evs[] = {io.up_done[0], io.up_done[1], io.res_ready, io.down_done};
+  for (cudaEvent_t ev : evs)
+    if (ev) cudaEventDestroy(ev);
+  if (io.up) cudaStreamDestroy(io.up);
+  if (io.down) cudaStreamDestroy(io.down);
+  io = LaneIO();
+}
+static cudaError_t grow(void*& p, size_t& cap, size_t bytes) {
+  if (cap >= bytes) return cudaSuccess;
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+  cudaError_t e = cudaMalloc(&p, bytes + bytes / 8);
+  if (e == cudaSuccess) cap = bytes + bytes / 8;
+  return e;
+}
 
 extern "C" {
 
@@ -687,12 +760,15 @@ int iftwt_batch_create(iftwt_batch** out, int device, int lanes) {
     }
     b->lanes.push_back(c);
   }
+  b->io.resize(b->lanes.size());
   *out = b;
   return IFTWT_OK;
 }
 
 void iftwt_batch_destroy(iftwt_batch* b) {
   if (!b) return;
+  cudaSetDevice(b->device);
+  for (LaneIO& io : b->io) lane_io_free(io);
   for (iftwt_ctx* c : b->lanes) iftwt_destroy(c);
   delete b;
 }
@@ -718,24 +794,108 @@ int iftwt_batch_segment(iftwt_batch* b, const void* const* clouds, const size_t*
   std::atomic<size_t> next(0);
   std::atomic<int> first_rc(IFTWT_OK);
   std::vector<std::string> errs(b->lanes.size());
-  auto work = [&](size_t lane) {
+  auto fail = [&](size_t lane, size_t i, int rc, const std::string& what) {
+    errs[lane] = "cloud " + std::to_string(i) + ": " + what;
+    int expected = IFTWT_OK;
+    first_rc.compare_exchange_strong(expected, rc);
+  };
+  auto work_device = [&](size_t lane) {
     iftwt_ctx* c = b->lanes[lane];
     while (first_rc.load() == IFTWT_OK) {
       const size_t i = next.fetch_add(1);
       if (i >= B) break;
-      int rc = clouds_on_device ? iftwt_set_cloud_device(c, clouds[i], n[i])
-                                : iftwt_set_cloud(c, clouds[i], 16, n[i], 0, 12);
+      int rc = iftwt_set_cloud_device(c, clouds[i], n[i]);
       size_t ns = 0;
       if (rc == IFTWT_OK)
         rc = iftwt_segment(c, params, cost ? cost[i] : nullptr, label ? label[i] : nullptr, &ns);
       if (rc != IFTWT_OK) {
-        errs[lane] = "cloud " + std::to_string(i) + ": " + c->err;
-        int expected = IFTWT_OK;
-        first_rc.compare_exchange_strong(expected, rc);
+        fail(lane, i, rc, c->err);
         break;
       }
       if (n_seeds) n_seeds[i] = ns;
     }
+  };
+  // host clouds: uploads and downloads in the lane's own copy streams (LaneIO above)
+  auto work_host = [&](size_t lane) {
+    iftwt_ctx* c = b->lanes[lane];
+    LaneIO& io = b->io[lane];
+    cudaSetDevice(b->device);
+#define LANE_CU(i_, expr)                                                            \
+  {                                                                                  \
+    cudaError_t e_ = (expr);                                                         \
+    if (e_ != cudaSuccess) {                                                         \
+      fail(lane, (i_), IFTWT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+      break;                                                                         \
+    }                                                                                \
+  }
+    bool down_pending = false;
+    do {
+      LANE_CU(0, lane_io_setup(io));
+      size_t i = next.fetch_add(1);
+      if (i >= B) break;
+      if (!clouds[i] || n[i] == 0) {
+        fail(lane, i, IFTWT_ERR_INVALID, "bad cloud");
+        break;
+      }
+      LANE_CU(i, grow(io.in[0], io.in_cap[0], n[i] * 16));
+      LANE_CU(i, cudaMemcpyAsync(io.in[0], clouds[i], n[i] * 16, cudaMemcpyHostToDevice, io.up));
+      LANE_CU(i, cudaEventRecord(io.up_done[0], io.up));
+      int cur = 0;
+      while (true) {
+        // the lane's next cloud starts moving now (the staging buffer it goes to was last read by a copy of
+        // the compute stream that iftwt_segment has long synchronised on)
+        size_t inext = B;
+        if (first_rc.load() == IFTWT_OK) inext = next.fetch_add(1);
+        if (inext < B) {
+          if (!clouds[inext] || n[inext] == 0) {
+            fail(lane, inext, IFTWT_ERR_INVALID, "bad cloud");
+            break;
+          }
+          LANE_CU(inext, grow(io.in[cur ^ 1], io.in_cap[cur ^ 1], n[inext] * 16));
+          LANE_CU(inext, cudaMemcpyAsync(io.in[cur ^ 1], clouds[inext], n[inext] * 16, cudaMemcpyHostToDevice, io.up));
+          LANE_CU(inext, cudaEventRecord(io.up_done[cur ^ 1], io.up));
+        }
+        LANE_CU(i, cudaStreamWaitEvent(c->stream, io.up_done[cur], 0));
+        int rc = iftwt_set_cloud_device(c, io.in[cur], n[i]);
+        size_t ns = 0;
+        if (rc == IFTWT_OK) rc = iftwt_segment(c, params, nullptr, nullptr, &ns);
+        if (rc != IFTWT_OK) {
+          fail(lane, i, rc, c->err);
+          break;
+        }
+        if (n_seeds) n_seeds[i] = ns;
+        uint32_t* co = cost ? cost[i] : nullptr;
+        uint32_t* la = label ? label[i] : nullptr;
+        if (co || la) {
+          if (io.res_cap < n[i] * 8) {
+            if (down_pending) LANE_CU(i, cudaStreamSynchronize(io.down));
+            LANE_CU(i, grow(io.res, io.res_cap, n[i] * 8));
+          }
+          // cost | label leave the ctx (its buffers belong to the next cloud from here on) ...
+          if (down_pending) LANE_CU(i, cudaStreamWaitEvent(c->stream, io.down_done, 0));
+          LANE_CU(i, cudaMemcpyAsync(io.res, c->out_a.p, n[i] * 8, cudaMemcpyDeviceToDevice, c->stream));
+          LANE_CU(i, cudaEventRecord(io.res_ready, c->stream));
+          // ... and go home in the download stream while the next cloud runs
+          LANE_CU(i, cudaStreamWaitEvent(io.down, io.res_ready, 0));
+          if (co) LANE_CU(i, cudaMemcpyAsync(co, io.res, n[i] * 4, cudaMemcpyDeviceToHost, io.down));
+          if (la)
+            LANE_CU(i, cudaMemcpyAsync(la, (const uint32_t*)io.res + n[i], n[i] * 4, cudaMemcpyDeviceToHost, io.down));
+          LANE_CU(i, cudaEventRecord(io.down_done, io.down));
+          down_pending = true;
+        }
+        if (inext >= B) break;
+        i = inext;
+        cur ^= 1;
+      }
+    } while (false);
+#undef LANE_CU
+    // the caller's buffers are his again when this returns, whatever happened
+    if (io.up) cudaStreamSynchronize(io.up);
+    if (io.down) cudaStreamSynchronize(io.down);
+  };
+  auto work = [&](size_t lane) {
+    if (clouds_on_device) work_device(lane);
+    else work_host(lane);
   };
   std::vector<std::thread> th;
   for (size_t l = 1; l < b->lanes.size() && l < B; ++l) th.emplace_back(work, l);

@@ -116,6 +116,8 @@ struct iftwt_ctx {
 
 int ctx_fail(iftwt_ctx* c, int code, const char* fmt, ...);
 int dev_ensure(iftwt_ctx* c, DevBuf& b, size_t bytes);
+// device words -> the ctx's mapped pinned mirrors (h_scalars / h_hist), written by a kernel: no copy engine
+int host_fetch(iftwt_ctx* c, void* h_dst, const void* d_src, size_t bytes);
 
 #define CU_TRY(ctx, expr)                                                             \
   do {                                                                                \

@@ -138,8 +138,8 @@ int graph_build(iftwt_ctx* c) {
     c->stats.kernel_launches += 2;
   }
   u32* hs = (u32*)c->h_scalars;
-  CU_TRY(c, cudaMemcpyAsync(hs + 54, roff + n, 4, cudaMemcpyDeviceToHost, c->stream));
-  CU_TRY(c, cudaMemcpyAsync(hs + 52, c->scalars.as<int>() + 52, 8, cudaMemcpyDeviceToHost, c->stream));
+  TRY(host_fetch(c, hs + 54, roff + n, 4));
+  TRY(host_fetch(c, hs + 52, c->scalars.as<int>() + 52, 8));
   CU_TRY(c, cudaStreamSynchronize(c->stream));
   const size_t n_rev = hs[54];
   const size_t n_fwd = *(unsigned long long*)(hs + 52);

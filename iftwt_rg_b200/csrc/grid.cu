@@ -213,6 +213,11 @@ __global__ void hash_build_kernel(const u64* __restrict__ cell_key, u32 n_cells,
 }
 
 __global__ void set_u32_kernel(u32* p, u32 v) { *p = v; }
+// the device scratch words of a grid build: bbox accumulators (ordered ints) + zeroed counters
+__global__ void scalars_reset_kernel(int* sc) {
+  const int i = threadIdx.x;
+  sc[i] = i < 3 ? 0x7FFFFFFF : (i < 6 ? (int)0x80000000 : 0);
+}
 
 // ---------------------------------------------------------------------------
 static double env_double(const char* name, double dflt) {
@@ -233,13 +238,10 @@ int grid_build(iftwt_ctx* c, int k) {
   int* hs = (int*)c->h_scalars;
 
   // --- bounding box ---
-  hs[0] = hs[1] = hs[2] = 0x7FFFFFFF;
-  hs[3] = hs[4] = hs[5] = (int)0x80000000;
-  for (int i = 6; i < 128; ++i) hs[i] = 0;
-  CU_TRY(c, cudaMemcpyAsync(sc, hs, 128 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  LAUNCH(c, scalars_reset_kernel, 1, 128, 0, sc);
   LAUNCH(c, bbox_kernel, c->sm_count * 8, 256, 0, pts, n, sc);
   CHECK_LAUNCH(c);
-  CU_TRY(c, cudaMemcpyAsync(hs, sc, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  TRY(host_fetch(c, hs, sc, 8 * sizeof(int)));
   CU_TRY(c, cudaStreamSynchronize(c->stream));
   if (hs[6] != 0)
     return ctx_fail(c, IFTWT_ERR_NONFINITE, "cloud holds %d non-finite points", hs[6]);
@@ -285,8 +287,8 @@ int grid_build(iftwt_ctx* c, int k) {
     CU_TRY(c, cudaMemsetAsync(c->occ_hist.p, 0, 17 * OCC_BINS * 4, c->stream));
     LAUNCH(c, occupancy_kernel, div_up(n_samples, 128), 128, 0, k1, m, stride, n_samples, sums, c->occ_hist.as<u32>());
     CHECK_LAUNCH(c);
-    CU_TRY(c, cudaMemcpyAsync(hs + 80, sums, 17 * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU_TRY(c, cudaMemcpyAsync(c->h_hist, c->occ_hist.p, 17 * OCC_BINS * 4, cudaMemcpyDeviceToHost, c->stream));
+    TRY(host_fetch(c, hs + 80, sums, 17 * 8));
+    TRY(host_fetch(c, c->h_hist, c->occ_hist.p, 17 * OCC_BINS * 4));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     const unsigned long long* hh = (const unsigned long long*)(hs + 80);
     double ppc[17];
@@ -420,7 +422,7 @@ int grid_build(iftwt_ctx* c, int k) {
                                                  c->cell_cnt.as<u32>(), d_nruns, (int)n, c->stream));
     c->stats.kernel_launches += 2;
   }
-  CU_TRY(c, cudaMemcpyAsync(hs + 40, d_nruns, sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
+  TRY(host_fetch(c, hs + 40, d_nruns, sizeof(u32)));
   CU_TRY(c, cudaStreamSynchronize(c->stream));
   u32 n_cells = (u32)hs[40];
   if (n_cells == 0 || n_cells > n) return ctx_fail(c, IFTWT_ERR_CUDA, "cell table build failed");

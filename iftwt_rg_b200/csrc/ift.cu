@@ -364,8 +364,8 @@ int ift_run(iftwt_ctx* c, const float* d_w_orig, const u32* d_seeds_orig, size_t
   }
   LAUNCH(c, ift_segments_kernel, 3, 256, 0, w16_sorted, n, d_seg);
   CHECK_LAUNCH(c);
-  CU_TRY(c, cudaMemcpyAsync(hs + 128, d_seg, 513 * 4, cudaMemcpyDeviceToHost, c->stream));
-  CU_TRY(c, cudaMemcpyAsync(hs + 64, d_bad, 8, cudaMemcpyDeviceToHost, c->stream));
+  TRY(host_fetch(c, hs + 128, d_seg, 513 * 4));
+  TRY(host_fetch(c, hs + 64, d_bad, 8));
   CU_TRY(c, cudaStreamSynchronize(c->stream));
   if (hs[64])
     return ctx_fail(c, IFTWT_ERR_WEIGHTS, "%u IFT weights are negative, NaN or not integer valued", hs[64]);

@@ -683,7 +683,7 @@ int knn_run(iftwt_ctx* c, int k) {
   }
   CHECK_LAUNCH(c);
   int* hs = (int*)c->h_scalars;
-  CU_TRY(c, cudaMemcpyAsync(hs + 48, fb_count, 4, cudaMemcpyDeviceToHost, c->stream));
+  TRY(host_fetch(c, hs + 48, fb_count, 4));
   c->knn_k = k;
   return IFTWT_OK;
 }

@@ -570,7 +570,7 @@ int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p) {
     CHECK_LAUNCH(c);
   }
   c->rg_pre_valid = false;  // the union-find is consumed (flattened) below
-  CU_TRY(c, cudaMemcpyAsync(hs + 56, d_cnt, 4, cudaMemcpyDeviceToHost, c->stream));
+  TRY(host_fetch(c, hs + 56, d_cnt, 4));
   // 3. component min rank, then label-min over one-way arcs
   CU_TRY(c, cudaMemsetAsync(L, 0xFF, (size_t)n * 8, c->stream));
   u32* root = c->vals_alt.as<u32>();  // free again once the ranks are scattered
@@ -595,7 +595,7 @@ int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p) {
     }
     CU_TRY(c, cudaMemsetAsync(d_m, 0, 4, c->stream));
     LAUNCH(c, rg_arcs_to_roots_kernel, div_up(n_oneway, 256), 256, 0, root, n_oneway, arc_u, arc_v, cu, cv, d_m);
-    CU_TRY(c, cudaMemcpyAsync(hs + 57, d_m, 4, cudaMemcpyDeviceToHost, c->stream));
+    TRY(host_fetch(c, hs + 57, d_m, 4));
     u32* d_changed = sc + 60;
     u32 grid_arcs = n_oneway;  // until the compact count has come back with the first sync
     while (true) {
@@ -605,7 +605,7 @@ int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p) {
         ++sweeps;
       }
       CHECK_LAUNCH(c);
-      CU_TRY(c, cudaMemcpyAsync(hs + 60, d_changed, 4, cudaMemcpyDeviceToHost, c->stream));
+      TRY(host_fetch(c, hs + 60, d_changed, 4));
       CU_TRY(c, cudaStreamSynchronize(c->stream));
       grid_arcs = hs[57];
       if (hs[60] == 0) break;
@@ -624,7 +624,7 @@ int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p) {
          (u32)max(p->min_cluster_size, 0), (u32)max(p->max_cluster_size, 0), keep, sc + 61, sc + 62, kept_key,
          kept_vertex);
   CHECK_LAUNCH(c);
-  CU_TRY(c, cudaMemcpyAsync(hs + 61, sc + 61, 8, cudaMemcpyDeviceToHost, c->stream));
+  TRY(host_fetch(c, hs + 61, sc + 61, 8));
   CU_TRY(c, cudaStreamSynchronize(c->stream));
   const u32 n_kept = hs[62];
   c->stats.rg_segments = hs[61];
