@@ -80,7 +80,12 @@ __device__ __forceinline__ void cell_queries(const CellWarp& w, const float* __r
   const float target = fminf(margin * (float)k + 2.f, 0.5f * (float)(k + CS));
   const float tiny = tau0 * 1e-6f;
   const float grow = margin + __fdividef(2.f, (float)k);
-  float tau = tau0;
+  const bool small = M <= CS;  // every staged candidate survives: the threshold stays at +inf
+  float tau = small ? INFINITY : tau0;
+  // completeness bounds of the cell's first 32 queries, fetched once: a load at the end of every query sat on
+  // its dependency chain (6 % of the kernel's stall samples on that line)
+  const float qb_first = lane < (int)w.qn ? qb2[w.qs + lane] : 0.f;
+  constexpr int NB = RR < 4 ? 2 : RR < 8 ? 3 : RR < 16 ? 4 : 5;  // bits of a lane's survivor count
 
   for (u32 q = 0; q < w.qn; ++q) {
     const float4 Q = w.s_pts[w.qoff + q];
@@ -93,15 +98,12 @@ __device__ __forceinline__ void cell_queries(const CellWarp& w, const float* __r
       d[r] = dist2_exact(Q.x, Q.y, Q.z, P.x, P.y, P.z);
     }
     // ---- threshold search: k <= #{d < tau} <= CS (candidate count ~ linear in tau on a surface) ----
-    int cnt = M;
-    bool ok = true;
-    if (M <= CS) {
-      tau = INFINITY;
-    } else {
-      ok = false;
+    int cnt = 0, cl = 0;
+    bool ok = false;
+    {
       float lo = 0.f, hi = INFINITY, t = tau, flo = 0.f, fhi = (float)M;
       for (int it = 0; it < 24; ++it) {
-        int cl = 0;  // counted per lane, summed by one warp reduction (2 instead of 4 instructions per round)
+        cl = 0;  // counted per lane, summed by one warp reduction (2 instead of 4 instructions per round)
 #pragma unroll
         for (int r = 0; r < RR; ++r) cl += (d[r] < t) ? 1 : 0;
         cnt = __reduce_add_sync(FULL, cl);
@@ -130,22 +132,22 @@ __device__ __forceinline__ void cell_queries(const CellWarp& w, const float* __r
     }
     bool done = false;
     if (ok) {
-      // ---- compact the survivors (d2 bits, slot) into shared memory ----
-      int base = 0;
+      // ---- compact the survivors (d2 bits, slot) into shared memory.  The search has left every lane its
+      // own survivor count: the lane's first list position is the exclusive prefix of those counts (one ballot
+      // per bit of the count), and its survivors follow each other — per round one compare, two predicated
+      // stores and an increment, instead of a ballot + popc pair per round.  (The list is lane-major now; its
+      // order never mattered: positions only name the survivors, ties go through the (d2, index) ranking.) ----
+      int pos = 0;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) pos += __popc(__ballot_sync(FULL, (cl >> b) & 1) & lt_mask) << b;
 #pragma unroll
       for (int r = 0; r < RR; ++r) {
-        const bool p = d[r] < tau;
-        const unsigned m = __ballot_sync(FULL, p);
-        const int pos = base + __popc(m & lt_mask);
-        if (p) {
+        if (d[r] < tau) {
           w.s_d2[pos] = __float_as_uint(d[r]);
           w.s_slot[pos] = (u32)(lane + 32 * r);
+          ++pos;
         }
-        base += __popc(m);
       }
-      // pad the survivor list to a multiple of eight with a value no key is below, so that the
-      // ranking loop below runs on whole pairs of uint4 words only
-      if (lane < 7 && cnt + lane < CS) w.s_d2[cnt + lane] = 0xFFFFFFFFu;
       __syncwarp();
       u32 kb = 0;  // bits of the k-th distance (set by the lane that owns it)
       bool ranked = false;
@@ -212,6 +214,10 @@ __device__ __forceinline__ void cell_queries(const CellWarp& w, const float* __r
         }
       }
       if (!ranked) {
+      // pad the survivor list to a multiple of eight with a value no key is below, so that the
+      // ranking loop below runs on whole pairs of uint4 words only
+      if (lane < 7 && cnt + lane < CS) w.s_d2[cnt + lane] = 0xFFFFFFFFu;
+      __syncwarp();
       // ---- rank = output slot.  Ranks are counted on d2 alone (non-negative floats order
       // as unsigned ints); an exact d2 tie makes two ranks collide, which shows as a rank
       // sum below cnt(cnt-1)/2 and sends the query through the full (d2, index) compare. ----
@@ -273,11 +279,11 @@ __device__ __forceinline__ void cell_queries(const CellWarp& w, const float* __r
       }
       }  // !ranked
       const float kd2 = __uint_as_float(__reduce_max_sync(FULL, kb));
-      done = kd2 <= qb2[qid];
-      tau = fmaxf(kd2 * grow, tiny);
+      done = kd2 <= (q < 32u ? __shfl_sync(FULL, qb_first, (int)q) : qb2[qid]);
+      tau = small ? INFINITY : fmaxf(kd2 * grow, tiny);
       __syncwarp();  // the next query's compaction overwrites the lists read above
     } else {
-      tau = tau0;
+      tau = small ? INFINITY : tau0;
     }
     // bit 31: the one-ring block is known to be too small, the general path starts at stage 1
     if (!done && lane == 0) fb_list[atomicAdd(fb_count, 1u)] = ok ? (qid | 0x80000000u) : qid;
