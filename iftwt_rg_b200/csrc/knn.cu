@@ -179,6 +179,12 @@ __device__ __forceinline__ void cell_queries(const CellWarp& w, const float* __r
         CX(7, l4);  CX(2, l2);  CX(1, l1);                    // 8
         CX(15, l8); CX(4, l4);  CX(2, l2); CX(1, l1);         // 16
         CX(31, l16); CX(8, l8); CX(4, l4); CX(2, l2); CX(1, l1);  // 32: ka and kc are sorted runs
+        // (When cnt <= 48 — three quarters of cfg3's queries — kc is a sorted run of 16 followed by fillers and
+        // only ka would have to be merged here.  Measured and rejected: the warp-uniform branch for it took the
+        // kernel from 48 to 56 registers, four blocks per SM instead of five: 4.44 -> 4.84 ms; held at 48 by
+        // __launch_bounds__ it spilled: 4.62 ms.  Also rejected: the comparison ranking below as a real call
+        // (__noinline__) for k <= 32, to take its ~600 cold instructions out of this loop's instruction
+        // stream: the call convention cost 64 registers, or 28 bytes of spills at 48: 5.30 ms.)
         {  // 64: position p of the first run against position 63 - p = second run, lane 31 - p
           const u32 tc = __shfl_xor_sync(FULL, kc, 31), ta = __shfl_xor_sync(FULL, ka, 31);
           ka = min(ka, tc);
@@ -296,6 +302,8 @@ __device__ __forceinline__ void cell_queries(const CellWarp& w, const float* __r
 // answered by a SECOND launch of the same code with a larger staging buffer (fewer warps resident,
 // but few cells) instead of by the general path, which costs ~8 times as much per query.
 template <int E, int CAP, bool SECOND>  // E = CS / 32 survivor slots per lane
+// (k <= 32, first launch: five blocks per SM is what the shared memory allows and the registers must follow —
+// 48 today.  Check -Xptxas -v after every change to this kernel.)
 __global__ void __launch_bounds__(KNN_WARPS_OF(E) * 32)
 knn_cell_kernel(GridView g, const float4* __restrict__ spts, const float* __restrict__ qb2, int k,
                 float tau0, float margin, u32* __restrict__ nbr, float* __restrict__ nd2, u64* __restrict__ kth,
