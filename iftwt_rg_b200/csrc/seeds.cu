@@ -191,6 +191,102 @@ rg_classify_kernel(const u32* __restrict__ nbr, const float* __restrict__ nd2, c
   }
 }
 
+// rg_classify_kernel for a neighbourhood size that divides 32 (KK = 16, 32: every BASELINE config).  A round of
+// 32 entries is then the whole row of one vertex (or of two): the three masks of a vertex are three ballots
+// over the round, kept by the lane that owns the vertex — no flag bytes through shared memory, no 32-step loop
+// per lane to assemble them, no division to find (vertex, j) of an entry.  The generic kernel spent 21 % of its
+// instructions on that bookkeeping and 26 % on the flags (ncu source page, round 2): 112 -> ~60 per vertex.
+template <bool FUSED, int RGA_B, int MINB, int KK>
+__global__ void __launch_bounds__(RGA_WARPS * 32, MINB)
+rg_classify_pow2_kernel(const u32* __restrict__ nbr, const float* __restrict__ nd2, const u64* __restrict__ kth,
+                        const float4* __restrict__ spts, u64* __restrict__ ow_mask, const float4* __restrict__ nrm,
+                        u32 n, float cos_thr, u64* __restrict__ hook_mask, u64* __restrict__ list_mask,
+                        u32* __restrict__ rdeg, unsigned long long* __restrict__ n_fwd, u32* __restrict__ parent) {
+  static_assert(KK == 16 || KK == 32, "one or two vertices per round");
+  constexpr int VPR = 32 / KK;        // vertices per round
+  constexpr u32 KM = KK == 32 ? 0xFFFFFFFFu : ((1u << (KK & 31)) - 1u);
+  __shared__ float4 s_nu_all[RGA_WARPS][32];
+  __shared__ u64 s_aux_all[RGA_WARPS][32];
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4* s_nu = s_nu_all[warp];   // normal of each tile vertex
+  u64* s_aux = s_aux_all[warp];    // FUSED: original index; else: the one-way mask
+  const u32 u0 = (blockIdx.x * RGA_WARPS + warp) * 32u;
+  if (u0 >= n) return;  // warps are independent: no block-level barrier below
+  const u32 u = u0 + lane;
+  if (u < n) {
+    s_nu[lane] = nrm[u];
+    s_aux[lane] = FUSED ? (u64)__float_as_uint(spts[u].w) : ow_mask[u];
+  }
+  __syncwarp();
+  const int sub = lane / KK, j = lane % KK;  // this lane's vertex within a round, its row entry
+  const size_t row0 = (size_t)u0 * KK;
+  u32 ow = 0, hk = 0, ls = 0, valid_cnt = 0;
+  for (int r0 = 0; r0 < KK; r0 += RGA_B) {  // KK rounds of 32 entries
+    u32 v[RGA_B];
+    float d2[RGA_B];
+    u64 kk[RGA_B];
+    float4 nv[RGA_B];
+#pragma unroll
+    for (int b = 0; b < RGA_B; ++b) {
+      const int p = (r0 + b) * VPR + sub;
+      const bool ok = r0 + b < KK && u0 + (u32)p < n;
+      const u32 e = (u32)lane + 32u * (u32)(r0 + b);
+      v[b] = ok ? nbr[row0 + e] : SID_NONE;
+      d2[b] = (FUSED && ok) ? nd2[row0 + e] : 0.f;
+      if (v[b] == u0 + (u32)p) v[b] = SID_NONE;  // the point itself
+    }
+#pragma unroll
+    for (int b = 0; b < RGA_B; ++b) {
+      const bool live = v[b] != SID_NONE;
+      kk[b] = (FUSED && live) ? kth[v[b]] : 0ull;
+      nv[b] = live ? nrm[v[b]] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int b = 0; b < RGA_B; ++b) {
+      const int p = (r0 + b) * VPR + sub;
+      const bool live = v[b] != SID_NONE;
+      bool oneway = false;
+      if (live) {
+        if (FUSED) {
+          const u64 key = ((u64)__float_as_uint(d2[b]) << 32) | s_aux[p];
+          oneway = key > kk[b];
+          if (oneway) atomicAdd(&rdeg[v[b]], 1u);
+        } else {
+          oneway = (s_aux[p] >> j) & 1ull;  // bit j: the tile vertex is NOT among the k nearest of v (graph.cu)
+        }
+      }
+      const bool smooth = live && smooth_pass(s_nu[p], nv[b], cos_thr);
+      const unsigned b_valid = __ballot_sync(FULL, live);
+      const unsigned b_ow = __ballot_sync(FULL, oneway);
+      const unsigned b_ls = __ballot_sync(FULL, smooth && oneway);
+      // smooth mutual, v < u: the twin arc is mutual and smooth too; one of the pair hooks
+      const unsigned b_hk = __ballot_sync(FULL, smooth && !oneway && v[b] < u0 + (u32)p);
+      valid_cnt += (u32)__popc(b_valid);
+      if (lane / VPR == r0 + b) {  // the lane that owns one of this round's vertices keeps its masks
+        const int sh = (lane % VPR) * KK;
+        ow = (b_ow >> sh) & KM;
+        ls = (b_ls >> sh) & KM;
+        hk = (b_hk >> sh) & KM;
+      }
+    }
+  }
+  if (u < n) {
+    if (FUSED) ow_mask[u] = (u64)ow;
+    // ECL-CC's initialisation: u starts under its nearest hook neighbour (a smaller id, so the
+    // links stay acyclic) — one plain store instead of two finds and a CAS
+    u32 par = u;
+    if (hk) {
+      par = nbr[(size_t)u * KK + (__ffs((int)hk) - 1)];
+      hk &= hk - 1;
+    }
+    parent[u] = par;
+    hook_mask[u] = (u64)hk;
+    list_mask[u] = (u64)ls;
+  }
+  if (FUSED && lane == 0 && valid_cnt) atomicAdd(n_fwd, (unsigned long long)valid_cnt);
+}
+
 #define HOOK_S 8
 __global__ void __launch_bounds__(256)
 rg_hook_kernel(const u32* __restrict__ nbr, const u64* __restrict__ hook_mask, const u64* __restrict__ list_mask,
@@ -201,11 +297,50 @@ rg_hook_kernel(const u32* __restrict__ nbr, const u64* __restrict__ hook_mask, c
   __shared__ u32 s_v[256 * HOOK_S];
   const u32 u = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  u64 mask = 0;
+  u64 mask = 0, hk = 0;
   if (u < n) {
-    const u32* row = nbr + (size_t)u * k;
-    u64 hk = hook_mask[u];
+    hk = hook_mask[u];
     mask = list_mask[u];
+  }
+  // ---- block-aggregated append of the one-way arcs.  FIRST: every thread does the same amount of work up to
+  // the barriers, and none of the variable-length union-find work below is followed by one (with the append
+  // last, 16 % of the kernel's stall samples sat on its __syncthreads: finished threads waiting for the
+  // block's slowest chase) ----
+  {
+    u32 cnt = (u32)__popcll(mask);
+    u32 incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      u32 tot = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        u32 c = s_warp[w];
+        s_warp[w] = tot;
+        tot += c;
+      }
+      s_base = tot ? atomicAdd(counter, tot) : 0u;
+    }
+    __syncthreads();
+    if (mask) {
+      u32 p = s_base + s_warp[warp] + (incl - cnt);
+      const u32* row = nbr + (size_t)u * k;
+      while (mask) {
+        int j = __ffsll((long long)mask) - 1;
+        mask &= mask - 1;
+        arc_u[p] = u;
+        arc_v[p] = row[j];
+        ++p;
+      }
+    }
+  }
+  if (hk) {
+    const u32* row = nbr + (size_t)u * k;
     u32 ru = 0xFFFFFFFFu;
     // HOOK_S arcs at a time: first all the row entries, then all their parents — independent
     // loads the hardware overlaps — and only then the finds and hooks, which are chains
@@ -246,38 +381,6 @@ rg_hook_kernel(const u32* __restrict__ nbr, const u64* __restrict__ hook_mask, c
           }
         }
       }
-    }
-  }
-  // ---- block-aggregated append of the one-way arcs ----
-  u32 cnt = (u32)__popcll(mask);
-  u32 incl = cnt;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    u32 t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  if (lane == 31) s_warp[warp] = incl;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    u32 tot = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
-      u32 c = s_warp[w];
-      s_warp[w] = tot;
-      tot += c;
-    }
-    s_base = tot ? atomicAdd(counter, tot) : 0u;
-  }
-  __syncthreads();
-  if (mask) {
-    u32 p = s_base + s_warp[warp] + (incl - cnt);
-    const u32* row = nbr + (size_t)u * k;
-    while (mask) {
-      int j = __ffsll((long long)mask) - 1;
-      mask &= mask - 1;
-      arc_u[p] = u;
-      arc_v[p] = row[j];
-      ++p;
     }
   }
 }
@@ -486,6 +589,24 @@ int fused_graph_rg_run(iftwt_ctx* c, const iftwt_rg_params* p) {
            c->nrm.as<float4>(), n, k, cos_thr, hook_mask, list_mask, c->g_deg.as<u32>(), d_nfwd,                     \
            c->rg_parent.as<u32>());                                                                                  \
   }
+#define RGA_LAUNCH_P2(B, MINB, KK)                                                                                 \
+  LAUNCH(c, (rg_classify_pow2_kernel<true, B, MINB, KK>), div_up(n, RGA_WARPS * 32), RGA_WARPS * 32, 0,            \
+         c->nbr.as<u32>(), c->nd2.as<float>(), c->kth.as<u64>(), c->spts.as<float4>(), c->ow_mask.as<u64>(),       \
+         c->nrm.as<float4>(), n, cos_thr, hook_mask, list_mask, c->g_deg.as<u32>(), d_nfwd, c->rg_parent.as<u32>())
+  const bool generic = getenv("IFTWT_RGA_GENERIC") && atoi(getenv("IFTWT_RGA_GENERIC")) != 0;
+  if (!generic && k == 32) {
+    // cfg3 on B200: (4 rounds in flight, 4 blocks per SM: 64 registers) 2.59 ms for classify + hook, (4, 5: 48
+    // registers) 2.52, (2, 6: 39 registers) 2.56, (4, 6: spills) 2.81; the generic kernel 2.89
+    if (variant == 1) RGA_LAUNCH_P2(4, 4, 32);
+    else if (variant == 3) RGA_LAUNCH_P2(2, 6, 32);
+    else RGA_LAUNCH_P2(4, 5, 32);
+  } else if (!generic && k == 16) {
+    // cfg3 on B200: (4 rounds in flight, 4 blocks per SM: 64 registers) 2.59 ms for classify + hook, (4, 5: 48
+    // registers) 2.52, (2, 6: 39 registers) 2.56, (4, 6: spills) 2.81; the generic kernel 2.89
+    if (variant == 1) RGA_LAUNCH_P2(4, 4, 16);
+    else if (variant == 3) RGA_LAUNCH_P2(2, 6, 16);
+    else RGA_LAUNCH_P2(4, 5, 16);
+  } else
   switch (variant) {
     case 1: RGA_LAUNCH(4, 5); break;
     case 2: RGA_LAUNCH(4, 6); break;
@@ -495,6 +616,7 @@ int fused_graph_rg_run(iftwt_ctx* c, const iftwt_rg_params* p) {
     default: RGA_LAUNCH(4, 4); break;
   }
 #undef RGA_LAUNCH
+#undef RGA_LAUNCH_P2
   LAUNCH(c, rg_hook_kernel, div_up(n, 256), 256, 0, c->nbr.as<u32>(), hook_mask, list_mask, n, k,
          c->rg_parent.as<u32>(), d_cnt, arc_u, arc_u + (ne + 1));
   CHECK_LAUNCH(c);
@@ -560,11 +682,24 @@ int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p) {
     ENSURE(c, c->rg_masks, (size_t)n * 16);
     u64* hook_mask = c->rg_masks.as<u64>();
     u64* list_mask = hook_mask + n;
+    const bool generic = getenv("IFTWT_RGA_GENERIC") && atoi(getenv("IFTWT_RGA_GENERIC")) != 0;
+#define RGA_LAUNCH_P2N(KK)                                                                                         \
+  LAUNCH(c, (rg_classify_pow2_kernel<false, 4, 4, KK>), div_up(n, RGA_WARPS * 32), RGA_WARPS * 32, 0,             \
+         c->nbr.as<u32>(), (const float*)nullptr, (const u64*)nullptr, (const float4*)nullptr,                    \
+         c->ow_mask.as<u64>(), nrm, n, cos_thr, hook_mask, list_mask, (u32*)nullptr, (unsigned long long*)nullptr, \
+         parent)
+    if (!generic && k == 32) {
+      RGA_LAUNCH_P2N(32);
+    } else if (!generic && k == 16) {
+      RGA_LAUNCH_P2N(16);
+    } else {
     CU_TRY(c, cudaFuncSetAttribute(rg_classify_kernel<false, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)rga_smem_bytes(k)));
     LAUNCH(c, (rg_classify_kernel<false, 4, 4>), div_up(n, RGA_WARPS * 32), RGA_WARPS * 32, rga_smem_bytes(k),
            c->nbr.as<u32>(), (const float*)nullptr, (const u64*)nullptr, (const float4*)nullptr, c->ow_mask.as<u64>(),
            nrm, n, k, cos_thr, hook_mask, list_mask, (u32*)nullptr, (unsigned long long*)nullptr, parent);
+    }
+#undef RGA_LAUNCH_P2N
     LAUNCH(c, rg_hook_kernel, div_up(n, 256), 256, 0, c->nbr.as<u32>(), hook_mask, list_mask, n, k, parent, d_cnt,
            arc_u, arc_v);
     CHECK_LAUNCH(c);
