@@ -73,6 +73,10 @@ __device__ __forceinline__ u64 rg_key(const float4* __restrict__ nrm, const floa
 // the same root: a warp-per-vertex variant spent 19 ms in CAS retries); the arcs of the list
 // mask are appended to (arc_u, arc_v) with one global atomic per block.
 //
+// Measured and rejected (round 2): the tile's 32 rows staged in shared memory by coalesced loads before the hooks
+// (the scattered row[j] reads fetch 1.29 GB of DRAM sectors at 1 TB/s): 34 KB of shared memory per block, 62 %
+// occupancy instead of 97 %, every row read whether it is needed or not — classify + hook 2.48 -> 3.29 ms.
+//
 // One thread per vertex doing both (rows and distances read at a 4k-byte stride, two gathers
 // per arc each on its own line, finds and CAS in between) ran at 88 % L1 throughput with 45
 // long-scoreboard stall cycles per issue: 3.9 ms at 10 M points, k = 32
@@ -512,31 +516,43 @@ __global__ void rg_member_keys_kernel(const u32* __restrict__ seg_of, const u32*
 // the result is the literal left-to-right FP32 sum.  (Broadcasting through shuffles put a
 // shuffle on the dependency chain of every addition: 0.29 ms for 190 clusters.)
 #define CEN_WARPS 4
+#define CEN_DEPTH 4  // batches of 32 gathers in flight per warp: one ahead left every batch waiting ~0.4 us for
+                     // its gather (313 batches in a 10,000-point cluster: 0.13 ms for cfg3's 190 clusters)
 __global__ void __launch_bounds__(CEN_WARPS * 32)
 rg_centroid_kernel(const u32* __restrict__ members, const u32* __restrict__ kstart,
                    const u32* __restrict__ ksize, u32 n_kept,
                    const float4* __restrict__ pts_in, float4* __restrict__ centroid) {
-  __shared__ float4 s_p[CEN_WARPS][2][32];
+  __shared__ float4 s_p[CEN_WARPS][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const u32 c = blockIdx.x * CEN_WARPS + warp;
   if (c >= n_kept) return;
   const u32 b = kstart[c], cnt = ksize[c];
   float sx = 0.f, sy = 0.f, sz = 0.f;
-  float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (lane < cnt) nxt = pts_in[members[b + lane]];
-  int buf = 0;
-  for (u32 base = 0; base < cnt; base += 32, buf ^= 1) {
-    s_p[warp][buf][lane] = nxt;
-    __syncwarp();
-    if (base + 32 + lane < cnt) nxt = pts_in[members[b + base + 32 + lane]];  // next batch in flight
-    const int m = (int)min(32u, cnt - base);
-    const float4* q = s_p[warp][buf];
+  float4 nxt[CEN_DEPTH];
+#pragma unroll
+  for (int d = 0; d < CEN_DEPTH; ++d) {
+    nxt[d] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (32u * d + lane < cnt) nxt[d] = pts_in[members[b + 32u * d + lane]];
+  }
+  for (u32 base = 0; base < cnt; base += 32u * CEN_DEPTH) {
+#pragma unroll
+    for (int d = 0; d < CEN_DEPTH; ++d) {
+      const u32 bd = base + 32u * d;
+      if (bd >= cnt) break;
+      __syncwarp();  // the previous batch has been read by every lane
+      s_p[warp][lane] = nxt[d];
+      __syncwarp();
+      const u32 ahead = bd + 32u * CEN_DEPTH + lane;
+      if (ahead < cnt) nxt[d] = pts_in[members[b + ahead]];  // CEN_DEPTH batches ahead
+      const int m = (int)min(32u, cnt - bd);
+      const float4* q = s_p[warp];
 #pragma unroll 8
-    for (int t = 0; t < m; ++t) {
-      const float4 p = q[t];
-      sx += p.x;
-      sy += p.y;
-      sz += p.z;
+      for (int t = 0; t < m; ++t) {
+        const float4 p = q[t];
+        sx += p.x;
+        sy += p.y;
+        sz += p.z;
+      }
     }
   }
   if (lane == 0) {
