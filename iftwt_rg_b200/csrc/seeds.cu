@@ -434,38 +434,75 @@ __global__ void rg_arcs_to_roots_kernel(const u32* __restrict__ root, u32 m, con
     out_v[pos] = rv;
   }
 }
-// m is read on the device: the grid is sized for the uncompacted list
+// m is read on the device: the grid is sized for the uncompacted list.  A launch relaxes every arc
+// SWEEP_ITERS times: the labels are read past L1 (ld.cg — the atomics resolve in L2), so a thread sees what
+// the others have lowered meanwhile and a chain of improvements advances several arcs per launch.  The
+// fixpoint of a monotone min-propagation does not depend on the schedule; a launch in which nothing
+// changed has seen every arc satisfied by labels that never moved, i.e. the fixpoint.  (One relaxation per
+// launch needed 12 launches of ~15 us on cfg3.)
+#define SWEEP_ITERS 4
 __global__ void rg_sweep_kernel(const u32* __restrict__ arc_u, const u32* __restrict__ arc_v,
-                                const u32* __restrict__ m_ptr, u64* __restrict__ L, u32* __restrict__ changed) {
+                                const u32* __restrict__ m_ptr, u64* L, u32* __restrict__ changed) {
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= *m_ptr) return;
-  u32 ru = arc_u[i], rv = arc_v[i];
-  u64 a = L[ru];
-  if (a < L[rv]) {
-    atomicMin((unsigned long long*)&L[rv], (unsigned long long)a);
-    *changed = 1u;
+  const u32 ru = arc_u[i], rv = arc_v[i];
+  bool any = false;
+#pragma unroll 1
+  for (int it = 0; it < SWEEP_ITERS; ++it) {
+    const u64 a = __ldcg((const unsigned long long*)&L[ru]);
+    if (a < __ldcg((const unsigned long long*)&L[rv])) {
+      atomicMin((unsigned long long*)&L[rv], (unsigned long long)a);
+      any = true;
+    }
   }
+  if (any) *changed = 1u;
 }
 // per point: segment = the vertex whose key is L[root] (the segment's seed point); sizes are
-// counted at the seed vertex (warp-aggregated)
-__global__ void rg_sizes_kernel(const u32* __restrict__ root, const u64* __restrict__ L,
-                                const u32* __restrict__ inv, u32 n, u32* __restrict__ seg_of,
-                                u32* __restrict__ size_at_seed) {
+// counted at the seed vertex.  A wall or a floor is ONE segment of 10^5 points, so one counter took an
+// atomic from nearly every warp of the cloud (312 k serialised atomics on a handful of addresses: 0.28 ms):
+// a block of 1024 consecutive (Morton-adjacent) vertices mostly lies in one segment, so the count of the block's
+// first vertex's segment is gathered in shared memory and leaves as ONE atomic; the other segments of the
+// block are warp-aggregated as before.
+#define SIZES_THREADS 1024
+__global__ void __launch_bounds__(SIZES_THREADS)
+rg_sizes_kernel(const u32* __restrict__ root, const u64* __restrict__ L, const u32* __restrict__ inv, u32 n,
+                u32* __restrict__ seg_of, u32* __restrict__ size_at_seed) {
+  __shared__ u32 s_pivot, s_count;
   u32 v = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = v < n;
-  const unsigned act = __ballot_sync(0xffffffffu, valid);
-  if (!valid) return;
-  const u32 s = inv[(u32)L[root[v]]];  // low half of the key = original index of the seed point
-  seg_of[v] = s;
-  const unsigned grp = __match_any_sync(act, s);
-  if ((int)(threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(&size_at_seed[s], (u32)__popc(grp));
+  u32 s = 0xFFFFFFFFu;
+  if (valid) {
+    s = inv[(u32)L[root[v]]];  // low half of the key = original index of the seed point
+    seg_of[v] = s;
+  }
+  if (threadIdx.x == 0) {
+    s_pivot = s;  // the block's first vertex is always valid
+    s_count = 0u;
+  }
+  __syncthreads();
+  const u32 pivot = s_pivot;
+  const unsigned on_pivot = __ballot_sync(0xffffffffu, valid && s == pivot);
+  const int lane = threadIdx.x & 31;
+  if (lane == 0 && on_pivot) atomicAdd(&s_count, (u32)__popc(on_pivot));
+  const bool other = valid && s != pivot;
+  const unsigned act = __ballot_sync(0xffffffffu, other);
+  if (other) {
+    const unsigned grp = __match_any_sync(act, s);
+    if (lane == __ffs(grp) - 1) atomicAdd(&size_at_seed[s], (u32)__popc(grp));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_count) atomicAdd(&size_at_seed[pivot], s_count);
 }
 // keep[s] for every seed vertex s; the kept seeds' (key, vertex) pairs are appended in any
-// order — the sort that follows puts them in PCL's emission order (ascending key)
+// order — the sort that follows puts them in PCL's emission order (ascending key).  The segment count
+// leaves as one atomic per block (one per warp: 0.8 M atomics on one address, 0.15 ms).
 __global__ void rg_keep_flags_kernel(const u32* __restrict__ size_at_seed, const float4* __restrict__ nrm,
                                      const float4* __restrict__ spts, u32 n, u32 min_sz, u32 max_sz,
                                      u32* __restrict__ keep, u32* __restrict__ nseg, u32* __restrict__ n_kept,
                                      u64* __restrict__ kept_key, u32* __restrict__ kept_vertex) {
+  __shared__ u32 s_nseg;
+  if (threadIdx.x == 0) s_nseg = 0u;
+  __syncthreads();
   u32 v = blockIdx.x * blockDim.x + threadIdx.x;
   u32 s = v < n ? size_at_seed[v] : 0u;
   const bool any = s > 0;
@@ -474,7 +511,7 @@ __global__ void rg_keep_flags_kernel(const u32* __restrict__ size_at_seed, const
   const unsigned m = __ballot_sync(0xffffffffu, any);
   const unsigned mk = __ballot_sync(0xffffffffu, kp);
   const int lane = threadIdx.x & 31;
-  if (lane == 0 && m) atomicAdd(nseg, (u32)__popc(m));
+  if (lane == 0 && m) atomicAdd(&s_nseg, (u32)__popc(m));
   if (mk) {
     u32 base = 0;
     if (lane == __ffs(mk) - 1) base = atomicAdd(n_kept, (u32)__popc(mk));
@@ -485,6 +522,8 @@ __global__ void rg_keep_flags_kernel(const u32* __restrict__ size_at_seed, const
       kept_vertex[pos] = v;
     }
   }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_nseg) atomicAdd(nseg, s_nseg);
 }
 // kept cluster c = position of its seed in ascending key order
 __global__ void rg_kept_ids_kernel(const u32* __restrict__ kept_vertex_sorted, const u32* __restrict__ size_at_seed,
@@ -751,9 +790,9 @@ int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p) {
     u32 grid_arcs = n_oneway;  // until the compact count has come back with the first sync
     while (true) {
       CU_TRY(c, cudaMemsetAsync(d_changed, 0, 4, c->stream));
-      for (int b = 0; b < 4; ++b) {
+      for (int b = 0; b < 2; ++b) {
         LAUNCH(c, rg_sweep_kernel, div_up(grid_arcs ? grid_arcs : 1, 256), 256, 0, cu, cv, d_m, L, d_changed);
-        ++sweeps;
+        sweeps += SWEEP_ITERS;
       }
       CHECK_LAUNCH(c);
       TRY(host_fetch(c, hs + 60, d_changed, 4));
@@ -767,7 +806,8 @@ int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p) {
   // 4. sizes, filter, emission order (ascending key of the seed point = PCL's)
   CU_TRY(c, cudaMemsetAsync(size_at_seed, 0, (size_t)n * 4, c->stream));
   CU_TRY(c, cudaMemsetAsync(sc + 61, 0, 8, c->stream));  // [61] segments, [62] kept
-  LAUNCH(c, rg_sizes_kernel, div_up(n, 256), 256, 0, root, L, c->inv.as<u32>(), n, seg_of, size_at_seed);
+  LAUNCH(c, rg_sizes_kernel, div_up(n, SIZES_THREADS), SIZES_THREADS, 0, root, L, c->inv.as<u32>(), n, seg_of,
+         size_at_seed);
   u64* kept_key = c->keys.as<u64>();
   u64* kept_key_sorted = c->keys_alt.as<u64>();
   u32* kept_vertex = c->rg_rank.as<u32>();
