@@ -201,8 +201,8 @@ __device__ __forceinline__ float4 finish_normal(float a0, float a1, float a2, fl
 // Tile shape: C neighbours at a time, B gather rounds in flight per lane, W warps per block.
 // (C, B, W) = (16, 8, 4) was round 1's; the variants are selectable with IFTWT_NRM_VARIANT for the
 // tuning sweep (tools/tune.py), the default is the fastest measured on cfg3.
-template <int C, int B, int W>
-__global__ void __launch_bounds__(W * 32)
+template <int C, int B, int W, int MINB = 0>
+__global__ void __launch_bounds__(W * 32, MINB)
 normals_kernel(const float4* __restrict__ spts, const u32* __restrict__ nbr, u32 n, int k,
                float4* __restrict__ out) {
   constexpr int STRIDE = C * 3 + 1;
@@ -267,9 +267,9 @@ int normals_run(iftwt_ctx* c) {
   const u32 n = (u32)c->n;
   ENSURE(c, c->nrm, (size_t)n * 16);
   const int variant = getenv("IFTWT_NRM_VARIANT") ? atoi(getenv("IFTWT_NRM_VARIANT")) : 0;
-#define NRM_LAUNCH(C, B, W)                                                                                       \
-  LAUNCH(c, (normals_kernel<C, B, W>), div_up(n, W * 32), W * 32, 0, c->spts.as<float4>(), c->nbr.as<u32>(), n, \
-         c->knn_k, c->nrm.as<float4>())
+#define NRM_LAUNCH(C, B, W, ...)                                                                                  \
+  LAUNCH(c, (normals_kernel<C, B, W, ##__VA_ARGS__>), div_up(n, W * 32), W * 32, 0, c->spts.as<float4>(),        \
+         c->nbr.as<u32>(), n, c->knn_k, c->nrm.as<float4>())
   // cfg3 on B200 (tools/tune.py, gpurun_out/r2_tune1.jsonl): (16,8,4) 1.146 ms, (16,4,4) 1.125, (8,8,4) 1.100,
   // (8,4,8) 1.208, (8,8,8) 1.078, (8,4,4) 1.218, (16,8,2) 1.400
   switch (variant) {
@@ -279,7 +279,12 @@ int normals_run(iftwt_ctx* c) {
     case 4: NRM_LAUNCH(16, 8, 4); break;
     case 5: NRM_LAUNCH(8, 4, 4); break;
     case 6: NRM_LAUNCH(16, 8, 2); break;
-    default: NRM_LAUNCH(8, 8, 8); break;
+    case 7: NRM_LAUNCH(8, 8, 8, 6); break;
+    case 8: NRM_LAUNCH(8, 4, 8, 8); break;
+    case 9: NRM_LAUNCH(8, 8, 4, 12); break;
+    case 10: NRM_LAUNCH(8, 8, 8, 1); break;
+    case 11: NRM_LAUNCH(8, 8, 8, 5); break;
+    default: NRM_LAUNCH(8, 8, 8, 5); break;  // 48 registers without the 4-byte spill of the unbounded build: 1.07 -> 0.99 ms
   }
 #undef NRM_LAUNCH
   CHECK_LAUNCH(c);

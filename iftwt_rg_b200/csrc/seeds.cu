@@ -225,7 +225,7 @@ rg_classify_pow2_kernel(const u32* __restrict__ nbr, const float* __restrict__ n
   __syncwarp();
   const int sub = lane / KK, j = lane % KK;  // this lane's vertex within a round, its row entry
   const size_t row0 = (size_t)u0 * KK;
-  u32 ow = 0, hk = 0, ls = 0, valid_cnt = 0;
+  u32 ow = 0, hk = 0, ls = 0, valid_cnt = 0, par_first = SID_NONE;
   for (int r0 = 0; r0 < KK; r0 += RGA_B) {  // KK rounds of 32 entries
     u32 v[RGA_B];
     float d2[RGA_B];
@@ -265,26 +265,30 @@ rg_classify_pow2_kernel(const u32* __restrict__ nbr, const float* __restrict__ n
       const unsigned b_ow = __ballot_sync(FULL, oneway);
       const unsigned b_ls = __ballot_sync(FULL, smooth && oneway);
       // smooth mutual, v < u: the twin arc is mutual and smooth too; one of the pair hooks
-      const unsigned b_hk = __ballot_sync(FULL, smooth && !oneway && v[b] < u0 + (u32)p);
+      const bool hookable = smooth && !oneway && v[b] < u0 + (u32)p;
+      const unsigned b_hk = __ballot_sync(FULL, hookable);
+      // the hook neighbour with the SMALLEST id becomes the vertex's first parent (below): it reaches much
+      // further back along the Morton curve than the nearest one, so the initial forest is shallow
+      const unsigned seg = KK == 32 ? FULL : (KM << (sub * KK));
+      const u32 vmin = __reduce_min_sync(seg, hookable ? v[b] : SID_NONE);
+      const unsigned b_first = __ballot_sync(FULL, hookable && v[b] == vmin);
+      const u32 vmin_hi = VPR == 1 ? vmin : __shfl_sync(FULL, vmin, 16);  // the round's second vertex (KK == 16)
+      const u32 vmin_lo = VPR == 1 ? vmin : __shfl_sync(FULL, vmin, 0);
       valid_cnt += (u32)__popc(b_valid);
       if (lane / VPR == r0 + b) {  // the lane that owns one of this round's vertices keeps its masks
         const int sh = (lane % VPR) * KK;
         ow = (b_ow >> sh) & KM;
         ls = (b_ls >> sh) & KM;
-        hk = (b_hk >> sh) & KM;
+        hk = ((b_hk & ~b_first) >> sh) & KM;
+        par_first = (lane % VPR) ? vmin_hi : vmin_lo;
       }
     }
   }
   if (u < n) {
     if (FUSED) ow_mask[u] = (u64)ow;
-    // ECL-CC's initialisation: u starts under its nearest hook neighbour (a smaller id, so the
-    // links stay acyclic) — one plain store instead of two finds and a CAS
-    u32 par = u;
-    if (hk) {
-      par = nbr[(size_t)u * KK + (__ffs((int)hk) - 1)];
-      hk &= hk - 1;
-    }
-    parent[u] = par;
+    // ECL-CC's initialisation: u starts under one of its hook neighbours (a smaller id, so the links stay
+    // acyclic) — one plain store instead of two finds and a CAS
+    parent[u] = par_first != SID_NONE ? par_first : u;
     hook_mask[u] = (u64)hk;
     list_mask[u] = (u64)ls;
   }
@@ -295,7 +299,7 @@ rg_classify_pow2_kernel(const u32* __restrict__ nbr, const float* __restrict__ n
 __global__ void __launch_bounds__(256)
 rg_hook_kernel(const u32* __restrict__ nbr, const u64* __restrict__ hook_mask, const u64* __restrict__ list_mask,
                u32 n, int k, u32* __restrict__ parent, u32* __restrict__ counter, u32* __restrict__ arc_u,
-               u32* __restrict__ arc_v) {
+               u32* __restrict__ arc_v, int hook_jumps) {
   __shared__ u32 s_warp[8];
   __shared__ u32 s_base;
   __shared__ u32 s_v[256 * HOOK_S];
@@ -365,7 +369,18 @@ rg_hook_kernel(const u32* __restrict__ nbr, const u64* __restrict__ hook_mask, c
 #pragma unroll
       for (int q = 0; q < HOOK_S; ++q)
         if (q < m) sv[256 * q] = parent[sv[256 * q]];  // one step up: v itself is never needed again
-      if (ru == 0xFFFFFFFFu) ru = uf_find(parent, u);
+      // ... and HOOK_JUMPS more steps for all of them at once (a root is its own parent: harmless there).  The
+      // finds below walk one chain at a time; every step taken here is one round trip for the whole batch
+      // instead of one per arc.
+      u32 pu = ru == 0xFFFFFFFFu ? parent[u] : ru;
+#pragma unroll 1
+      for (int rep = 0; rep < hook_jumps; ++rep) {
+#pragma unroll
+        for (int q = 0; q < HOOK_S; ++q)
+          if (q < m) sv[256 * q] = parent[sv[256 * q]];
+        if (ru == 0xFFFFFFFFu) pu = parent[pu];
+      }
+      if (ru == 0xFFFFFFFFu) ru = uf_find(parent, pu);
       for (int q = 0; q < m; ++q) {
         u32 rv = sv[256 * q];
         if (rv == ru) continue;  // v hangs directly under u's representative
@@ -609,6 +624,11 @@ __global__ void rg_seed_ids_kernel(const u32* __restrict__ sid_sorted, const u32
 
 }  // namespace
 
+static int hook_jumps() {
+  const char* e = getenv("IFTWT_HOOK_JUMPS");
+  return e ? atoi(e) : 2;
+}
+
 // iftwt_segment fast path: graph mutuality + region-growing arcs in one pass.  Needs the k-NN
 // lists and the normals; leaves ow_mask / rdeg / n_fwd for graph_build and the union-find +
 // one-way arc list for seeds_run.
@@ -650,17 +670,17 @@ int fused_graph_rg_run(iftwt_ctx* c, const iftwt_rg_params* p) {
          c->nrm.as<float4>(), n, cos_thr, hook_mask, list_mask, c->g_deg.as<u32>(), d_nfwd, c->rg_parent.as<u32>())
   const bool generic = getenv("IFTWT_RGA_GENERIC") && atoi(getenv("IFTWT_RGA_GENERIC")) != 0;
   if (!generic && k == 32) {
-    // cfg3 on B200: (4 rounds in flight, 4 blocks per SM: 64 registers) 2.59 ms for classify + hook, (4, 5: 48
-    // registers) 2.52, (2, 6: 39 registers) 2.56, (4, 6: spills) 2.81; the generic kernel 2.89
-    if (variant == 1) RGA_LAUNCH_P2(4, 4, 32);
+    // cfg3 on B200, classify + hook: (4 rounds in flight, 4 blocks per SM: 64 registers) 2.36 ms, (4, 5: 48
+    // registers, a few spilled words since the smallest-id parent) 2.45; the generic kernel 2.89
+    if (variant == 1) RGA_LAUNCH_P2(4, 5, 32);
     else if (variant == 3) RGA_LAUNCH_P2(2, 6, 32);
-    else RGA_LAUNCH_P2(4, 5, 32);
+    else RGA_LAUNCH_P2(4, 4, 32);
   } else if (!generic && k == 16) {
-    // cfg3 on B200: (4 rounds in flight, 4 blocks per SM: 64 registers) 2.59 ms for classify + hook, (4, 5: 48
-    // registers) 2.52, (2, 6: 39 registers) 2.56, (4, 6: spills) 2.81; the generic kernel 2.89
-    if (variant == 1) RGA_LAUNCH_P2(4, 4, 16);
+    // cfg3 on B200, classify + hook: (4 rounds in flight, 4 blocks per SM: 64 registers) 2.36 ms, (4, 5: 48
+    // registers, a few spilled words since the smallest-id parent) 2.45; the generic kernel 2.89
+    if (variant == 1) RGA_LAUNCH_P2(4, 5, 16);
     else if (variant == 3) RGA_LAUNCH_P2(2, 6, 16);
-    else RGA_LAUNCH_P2(4, 5, 16);
+    else RGA_LAUNCH_P2(4, 4, 16);
   } else
   switch (variant) {
     case 1: RGA_LAUNCH(4, 5); break;
@@ -673,7 +693,7 @@ int fused_graph_rg_run(iftwt_ctx* c, const iftwt_rg_params* p) {
 #undef RGA_LAUNCH
 #undef RGA_LAUNCH_P2
   LAUNCH(c, rg_hook_kernel, div_up(n, 256), 256, 0, c->nbr.as<u32>(), hook_mask, list_mask, n, k,
-         c->rg_parent.as<u32>(), d_cnt, arc_u, arc_u + (ne + 1));
+         c->rg_parent.as<u32>(), d_cnt, arc_u, arc_u + (ne + 1), hook_jumps());
   CHECK_LAUNCH(c);
   c->mask_k = k;
   c->rdeg_k = k;
@@ -756,7 +776,7 @@ int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p) {
     }
 #undef RGA_LAUNCH_P2N
     LAUNCH(c, rg_hook_kernel, div_up(n, 256), 256, 0, c->nbr.as<u32>(), hook_mask, list_mask, n, k, parent, d_cnt,
-           arc_u, arc_v);
+           arc_u, arc_v, hook_jumps());
     CHECK_LAUNCH(c);
   }
   c->rg_pre_valid = false;  // the union-find is consumed (flattened) below
