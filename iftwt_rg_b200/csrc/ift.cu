@@ -180,7 +180,11 @@ __device__ __forceinline__ void ift_visit(u64* __restrict__ node, u32 level, u32
 // 6.23 ms: a barrier over 1184 resident blocks is no cheaper than a launch boundary); a pre-pass
 // that marks, per vertex, the forward neighbours that are not heavier, so that the level kernels
 // skip the arcs to still-closed neighbours (half of the forward visits) — the pre-pass and the
-// extra mask load cost more than the skipped visits saved (6.2 -> 7.1 ms).
+// extra mask load cost more than the skipped visits saved (6.2 -> 7.1 ms).  Round 2 repeated it with the mask made
+// for free — by the fused graph / region-growing pass, which has both ends of every arc in hand (one more 2-byte
+// gather per arc there), seeds patched in afterwards — and the level kernels skipping the row entry and the node
+// word of every masked arc: IFT 5.16 -> 5.10 ms, the graph pass 2.29 -> 2.63 ms.  Half the gathers gone and the
+// levels barely faster: they are bound by the length of the dependent chain per vertex, not by L2 sector rate.
 #define IFT_PEND 6
 #define IFT_AHEAD 2  // 3 / 4 rounds ahead spill at 32 registers: 5.84 / 5.95 ms against 5.70; 4 ahead at 40 registers: 6.2 ms
 template <int G>
