@@ -268,7 +268,9 @@ IFTWT_API void iftwt_batch_destroy(iftwt_batch* batch);
 IFTWT_API const char* iftwt_batch_last_error(const iftwt_batch* batch); /* batch may be NULL */
 IFTWT_API iftwt_ctx* iftwt_batch_ctx(iftwt_batch* batch, int lane);     /* e.g. for iftwt_get_stats */
 /* clouds[i]: n[i] packed float4 {x,y,z,intensity} records — DEVICE pointers when clouds_on_device != 0,
- * host pointers otherwise.  cost / label: B host pointers (each n[i] entries) or NULL; entries may be NULL.
+ * host pointers otherwise (pinned memory lets the copies run beside the kernels: every lane uploads its next
+ * cloud and downloads its previous results in copy streams of its own while the current cloud is segmented;
+ * pageable memory works, the copies then block the lane's host thread).  cost / label: B host pointers (each n[i] entries) or NULL; entries may be NULL.
  * n_seeds: B entries or NULL.  Returns the first error of any cloud. */
 IFTWT_API int iftwt_batch_segment(iftwt_batch* batch, const void* const* clouds, const size_t* n, size_t B,
                                   int clouds_on_device, const iftwt_segment_params* params, uint32_t* const* cost,
