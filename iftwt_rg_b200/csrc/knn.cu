@@ -102,11 +102,16 @@ __device__ __forceinline__ void cell_queries(const CellWarp& w, const float* __r
     bool ok = false;
     {
       float lo = 0.f, hi = INFINITY, t = tau, flo = 0.f, fhi = (float)M;
+#pragma unroll 1
       for (int it = 0; it < 24; ++it) {
         cl = 0;  // counted per lane, summed by one warp reduction (2 instead of 4 instructions per round)
 #pragma unroll
         for (int r = 0; r < RR; ++r) cl += (d[r] < t) ? 1 : 0;
         cnt = __reduce_add_sync(FULL, cl);
+        if ((unsigned)(cnt - k) <= (unsigned)(CS - k)) {  // k <= cnt <= CS: the usual first answer
+          ok = true;
+          break;
+        }
         const float fc = (float)cnt;
         if (cnt < k) {
           lo = t;
