@@ -74,13 +74,18 @@ __device__ __forceinline__ void cell_queries(const CellWarp& w, const float* __r
                                              u64* __restrict__ kth, u32* __restrict__ fb_list,
                                              u32* __restrict__ fb_count, int lane) {
   constexpr int CS = 32 * E;
+  // survivors the threshold search accepts.  E == 2 (17 <= k <= 32): at most 48, so that the second key of every
+  // lane >= 16 is a filler and the upper run of the sorting network is a sorted 16 + fillers — its five-step
+  // merge to a run of 32 is never needed (the same cut as a warp-uniform branch on cnt <= 48 cost registers and
+  // was slower; as a property of every query it costs a narrower window for the search instead)
+  constexpr int CSA = E == 2 ? 48 : CS;
   const unsigned FULL = 0xffffffffu;
   const unsigned lt_mask = (1u << lane) - 1u;
   const int M = w.M;
-  const float target = fminf(margin * (float)k + 2.f, 0.5f * (float)(k + CS));
+  const float target = fminf(margin * (float)k + 2.f, 0.5f * (float)(k + CSA));
   const float tiny = tau0 * 1e-6f;
   const float grow = margin + __fdividef(2.f, (float)k);
-  const bool small = M <= CS;  // every staged candidate survives: the threshold stays at +inf
+  const bool small = M <= CSA;  // every staged candidate survives: the threshold stays at +inf
   float tau = small ? INFINITY : tau0;
   // completeness bounds of the cell's first 32 queries, fetched once: a load at the end of every query sat on
   // its dependency chain (6 % of the kernel's stall samples on that line)
@@ -108,7 +113,7 @@ __device__ __forceinline__ void cell_queries(const CellWarp& w, const float* __r
 #pragma unroll
         for (int r = 0; r < RR; ++r) cl += (d[r] < t) ? 1 : 0;
         cnt = __reduce_add_sync(FULL, cl);
-        if ((unsigned)(cnt - k) <= (unsigned)(CS - k)) {  // k <= cnt <= CS: the usual first answer
+        if ((unsigned)(cnt - k) <= (unsigned)(CSA - k)) {  // k <= cnt <= CSA: the usual first answer
           ok = true;
           break;
         }
@@ -116,7 +121,7 @@ __device__ __forceinline__ void cell_queries(const CellWarp& w, const float* __r
         if (cnt < k) {
           lo = t;
           flo = fc;
-        } else if (cnt > CS) {
+        } else if (cnt > CSA) {
           hi = t;
           fhi = fc;
         } else {
@@ -183,13 +188,18 @@ __device__ __forceinline__ void cell_queries(const CellWarp& w, const float* __r
         CX(3, l2);  CX(1, l1);                                // 4
         CX(7, l4);  CX(2, l2);  CX(1, l1);                    // 8
         CX(15, l8); CX(4, l4);  CX(2, l2); CX(1, l1);         // 16
-        CX(31, l16); CX(8, l8); CX(4, l4); CX(2, l2); CX(1, l1);  // 32: ka and kc are sorted runs
-        // (When cnt <= 48 — three quarters of cfg3's queries — kc is a sorted run of 16 followed by fillers and
-        // only ka would have to be merged here.  Measured and rejected: the warp-uniform branch for it took the
-        // kernel from 48 to 56 registers, four blocks per SM instead of five: 4.44 -> 4.84 ms; held at 48 by
-        // __launch_bounds__ it spilled: 4.62 ms.  Also rejected: the comparison ranking below as a real call
-        // (__noinline__) for k <= 32, to take its ~600 cold instructions out of this loop's instruction
-        // stream: the call convention cost 64 registers, or 28 bytes of spills at 48: 5.30 ms.)
+#define CX1(mask, lower)                                       \
+  {                                                            \
+    const u32 ta = __shfl_xor_sync(FULL, ka, mask);            \
+    ka = (lower) ? min(ka, ta) : max(ka, ta);                  \
+  }
+        // 32: ka becomes a sorted run; kc (<= 16 survivors in lanes 0..15, fillers above) already is one
+        CX1(31, l16); CX1(8, l8); CX1(4, l4); CX1(2, l2); CX1(1, l1);
+        // (The same cut as a warp-uniform branch on cnt <= 48, with the search still accepting 64: 56 registers, four
+        // blocks per SM instead of five: 4.44 -> 4.84 ms; held at 48 by __launch_bounds__ it spilled: 4.62 ms.  Also
+        // rejected: the comparison ranking below as a real call (__noinline__) for k <= 32, to take its ~600 cold
+        // instructions out of this loop's instruction stream: the call convention cost 64 registers, or 28 bytes
+        // of spills at 48: 5.30 ms.)
         {  // 64: position p of the first run against position 63 - p = second run, lane 31 - p
           const u32 tc = __shfl_xor_sync(FULL, kc, 31), ta = __shfl_xor_sync(FULL, ka, 31);
           ka = min(ka, tc);
@@ -198,11 +208,6 @@ __device__ __forceinline__ void cell_queries(const CellWarp& w, const float* __r
         // k <= 32 here (E == 2): only the lower half is ever written, so only ka is sorted on
         // (five steps on one key instead of two); of the upper half only its minimum matters — it is the
         // successor of position 31 in the tie check
-#define CX1(mask, lower)                                       \
-  {                                                            \
-    const u32 ta = __shfl_xor_sync(FULL, ka, mask);            \
-    ka = (lower) ? min(ka, ta) : max(ka, ta);                  \
-  }
         CX1(16, l16); CX1(8, l8); CX1(4, l4); CX1(2, l2); CX1(1, l1);
 #undef CX1
 #undef CX
@@ -689,7 +694,8 @@ int knn_run(iftwt_ctx* c, int k) {
     // (cfg3): 1.05 -> 5.76 ms, 1.12 -> 5.77, 1.25 -> 5.87, 1.4 -> 6.01.  The 64-key network of E == 2 costs
     // the same for any cnt <= 64, so a wider margin only saves threshold iterations: 1.1 -> 5.13 ms,
     // 1.2 -> 5.10, 1.3 / 1.4 -> 5.09
-    const float margin = menv ? (float)atof(menv) : (E == 2 ? 1.3f : 1.1f);
+    // (E == 2 with at most 48 survivors accepted: 1.3 -> 4.36 ms, 1.2 -> 4.33, 1.15 -> 4.33)
+    const float margin = menv ? (float)atof(menv) : (E == 2 ? 1.2f : 1.1f);
     const unsigned blocks = div_up(g.n_cells, KNN_WARPS_OF(E));
     const int cap2 = E <= 2 ? KNN_CAP2 : 0;
     LAUNCH(c, kern, blocks, KNN_WARPS_OF(E) * 32, sm, g, spts, (const float*)c->qb2.as<float>(), k, tau0, margin,
