@@ -401,6 +401,10 @@ rg_hook_kernel(const u32* __restrict__ nbr, const u64* __restrict__ hook_mask, c
         }
       }
     }
+    // u hangs (well) below its representative: point it there.  Safe as path halving is — a vertex that is not a
+    // root never becomes one again and ru was an ancestor of u when it was read, so it still is; a ROOT must keep
+    // its own word, another thread may be hooking it this instant.  The flatten kernel then finds short chains.
+    if (ru != 0xFFFFFFFFu && ru != u) parent[u] = ru;
   }
 }
 
@@ -600,12 +604,26 @@ rg_centroid_kernel(const u32* __restrict__ members, const u32* __restrict__ ksta
       if (ahead < cnt) nxt[d] = pts_in[members[b + ahead]];  // CEN_DEPTH batches ahead
       const int m = (int)min(32u, cnt - bd);
       const float4* q = s_p[warp];
-#pragma unroll 8
-      for (int t = 0; t < m; ++t) {
-        const float4 p = q[t];
-        sx += p.x;
-        sy += p.y;
-        sz += p.z;
+      if (m == 32) {  // whole batch: eight broadcast reads ahead of the 24 dependent additions they feed
+#pragma unroll
+        for (int t0 = 0; t0 < 32; t0 += 8) {
+          float4 r[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) r[t] = q[t0 + t];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            sx += r[t].x;
+            sy += r[t].y;
+            sz += r[t].z;
+          }
+        }
+      } else {
+        for (int t = 0; t < m; ++t) {
+          const float4 p = q[t];
+          sx += p.x;
+          sy += p.y;
+          sz += p.z;
+        }
       }
     }
   }
