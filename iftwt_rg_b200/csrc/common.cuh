@@ -102,6 +102,7 @@ struct iftwt_ctx {
   size_t n_pairs = 0, n_regions = 0, pairs_vals_offset = 0;
   bool rag_valid = false;
   bool ift_valid = false;
+  bool ift_res_valid = false;  // ift_res holds the words of the current run (built on demand: ift_res_ensure)
   // --- voxel graph (builder A) ---
   DevBuf vx_keys, vx_rows, vx_cent, vx_hk, vx_hv;
   double voxel_size = 0.0;
@@ -198,6 +199,7 @@ int normals_run(iftwt_ctx* c);                                             // no
 int seeds_run(iftwt_ctx* c, const iftwt_rg_params* p);                     // seeds.cu
 int fused_graph_rg_run(iftwt_ctx* c, const iftwt_rg_params* p);
 int ift_run(iftwt_ctx* c, const float* d_w_orig /*or null*/, const u32* d_seeds_orig, size_t ns);  // ift.cu
+int ift_res_ensure(iftwt_ctx* c);
 
 // ---- device helpers ----
 #ifdef __CUDACC__

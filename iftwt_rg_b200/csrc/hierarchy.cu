@@ -159,6 +159,7 @@ int build_region_list(iftwt_ctx* c) {
 int region_adjacency_run(iftwt_ctx* c) {
   if (!c->ift_valid) return ctx_fail(c, IFTWT_ERR_STATE, "no IFT result on the device");
   if (c->rag_valid) return IFTWT_OK;
+  TRY(ift_res_ensure(c));
   const u32 n = (u32)c->n;
   GraphView g = graph_view(c);
   const u64* res = c->ift_res.as<u64>();
@@ -215,6 +216,7 @@ int region_adjacency_run(iftwt_ctx* c) {
 // c->h_info: area u32 [n_regions], height f32 [n_regions]; region list in c->h_seeds (second half)
 int region_info_run(iftwt_ctx* c) {
   if (!c->ift_valid) return ctx_fail(c, IFTWT_ERR_STATE, "no IFT result on the device");
+  TRY(ift_res_ensure(c));
   TRY(build_region_list(c));
   const u32 nr = (u32)c->n_regions;
   ENSURE(c, c->h_info, ((size_t)nr + 1) * 8);
@@ -228,6 +230,7 @@ int region_info_run(iftwt_ctx* c) {
 }
 
 int cluster_run(iftwt_ctx* c, int num_regions, u32* d_cluster_orig, size_t* n_clusters) {
+  TRY(ift_res_ensure(c));
   TRY(region_adjacency_run(c));
   TRY(build_region_list(c));
   const size_t S = c->n_regions, m = c->n_pairs;

@@ -316,14 +316,16 @@ ift_level_kernel(const u32* __restrict__ byw, u32 seg_begin, u32 seg_len, u32 le
   for (int o = G / 2; o > 0; o >>= 1) lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
   if (work && gl == 0 && lmin != LBL_NONE) node_offer(node, rt, ((u64)(level + 2u) << 32) | (u64)lmin);
 }
-// every vertex reads its component's word; unconquered vertices keep (500, self)
-__global__ void ift_resolve_kernel(u64* __restrict__ node, const u32* __restrict__ perm, u32 n,
-                                   u32* __restrict__ cost_o, u32* __restrict__ label_o, u64* __restrict__ res) {
-  u32 v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= n) return;
+// every vertex reads its component's word; unconquered vertices keep (500, self).  One thread per ORIGINAL
+// index: cost and label leave as coalesced stores and the component word is a gather (the per-sorted-vertex form
+// scattered two 4-byte stores per point — 640 MB of read-modify-write sectors, 0.25 ms at 10 M points).
+__global__ void ift_resolve_kernel(u64* __restrict__ node, const u32* __restrict__ inv, u32 n,
+                                   u32* __restrict__ cost_o, u32* __restrict__ label_o) {
+  u32 o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n) return;
+  const u32 v = inv[o];
   u32 r = v;
   const u64 x = node_find(node, r, node[v]);
-  const u32 o = perm[v];
   const u32 h = NODE_HI(x);
   u32 cst = IFTWT_MAX_COST, lbl = o;
   if (h < NODE_UNCONQ) {
@@ -332,6 +334,19 @@ __global__ void ift_resolve_kernel(u64* __restrict__ node, const u32* __restrict
   }
   cost_o[o] = cst;
   label_o[o] = lbl;
+}
+// (cost << 32 | label) per SORTED vertex, for the region hierarchy: built when it is first asked for
+__global__ void ift_res_kernel(u64* __restrict__ node, const u32* __restrict__ perm, u32 n, u64* __restrict__ res) {
+  u32 v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  u32 r = v;
+  const u64 x = node_find(node, r, node[v]);
+  const u32 h = NODE_HI(x);
+  u32 cst = IFTWT_MAX_COST, lbl = perm[v];
+  if (h < NODE_UNCONQ) {
+    cst = h < 2u ? 0u : h - 2u;
+    lbl = NODE_LO(x);
+  }
   res[v] = ((u64)cst << 32) | (u64)lbl;
 }
 
@@ -346,7 +361,6 @@ int ift_run(iftwt_ctx* c, const float* d_w_orig, const u32* d_seeds_orig, size_t
   const u32 n = (u32)c->n;
   ENSURE(c, c->ift_w, (size_t)n * 2 * 2 + 16);
   ENSURE(c, c->ift_byw, (size_t)n * 4 * 2);
-  ENSURE(c, c->ift_res, (size_t)n * 8);
   ENSURE(c, c->ift_wf, (size_t)n * 4);
   ENSURE(c, c->ift_node, (size_t)n * 8);
   u64* node = c->ift_node.as<u64>();
@@ -405,11 +419,23 @@ int ift_run(iftwt_ctx* c, const float* d_w_orig, const u32* d_seeds_orig, size_t
   CHECK_LAUNCH(c);
   u32* cost_o = c->out_a.as<u32>();
   u32* label_o = cost_o + n;
-  LAUNCH(c, ift_resolve_kernel, div_up(n, 256), 256, 0, node, c->perm.as<u32>(), n, cost_o, label_o,
-         c->ift_res.as<u64>());
+  LAUNCH(c, ift_resolve_kernel, div_up(n, 256), 256, 0, node, c->inv.as<u32>(), n, cost_o, label_o);
   CHECK_LAUNCH(c);
+  c->ift_res_valid = false;
   c->stats.ift_levels = levels;
   c->ift_valid = true;
   c->rag_valid = false;
+  return IFTWT_OK;
+}
+
+// the per-sorted-vertex result words the region hierarchy reads (hierarchy.cu); node[] keeps the run's state
+int ift_res_ensure(iftwt_ctx* c) {
+  if (!c->ift_valid) return ctx_fail(c, IFTWT_ERR_STATE, "no IFT result on the device");
+  if (c->ift_res_valid) return IFTWT_OK;
+  const u32 n = (u32)c->n;
+  ENSURE(c, c->ift_res, (size_t)n * 8);
+  LAUNCH(c, ift_res_kernel, div_up(n, 256), 256, 0, c->ift_node.as<u64>(), c->perm.as<u32>(), n, c->ift_res.as<u64>());
+  CHECK_LAUNCH(c);
+  c->ift_res_valid = true;
   return IFTWT_OK;
 }
