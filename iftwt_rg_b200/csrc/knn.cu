@@ -654,6 +654,110 @@ knn_general_kernel(GridView g, const float4* __restrict__ spts, const float4* __
   }
 }
 
+// A handful of external queries with k = 1 (the centroid snap of the seed stage: ~10^2 queries): one BLOCK per
+// query instead of one warp.  A centroid of a curved cluster lies off the surface, its block has to grow over
+// several stages, and a single warp scanning them was a 0.12 ms latency chain for 190 queries; eight warps share the
+// 27 super-cells of a stage.  Same stages, same stopping rule, same canonical (d2, original index) order as the
+// general path — the nearest point is the nearest point.
+__global__ void __launch_bounds__(256)
+knn_nearest_block_kernel(GridView g, const float4* __restrict__ spts, const float4* __restrict__ queries, u32 m,
+                         u32* __restrict__ out_sid, float* __restrict__ out_d2) {
+  __shared__ u32 s_ps[27], s_pe[27];
+  __shared__ u64 s_key[8];
+  __shared__ u32 s_sid[8];
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const u32 it = blockIdx.x;
+  if (it >= m) return;
+  const float4 Q = queries[it];
+  const double vx = ((double)Q.x - g.ox) * g.inv_cell, vy = ((double)Q.y - g.oy) * g.inv_cell,
+               vz = ((double)Q.z - g.oz) * g.inv_cell;
+  const int cx = min(g.dimx - 1, max(0, (int)floor(vx)));
+  const int cy = min(g.dimy - 1, max(0, (int)floor(vy)));
+  const int cz = min(g.dimz - 1, max(0, (int)floor(vz)));
+  u64 best = KEY_MAX;
+  u32 bsid = SID_NONE;
+  for (int j = 0;; ++j) {
+    const int sx = cx >> j, sy = cy >> j, sz = cz >> j;
+    const int sdx = ((g.dimx - 1) >> j) + 1, sdy = ((g.dimy - 1) >> j) + 1, sdz = ((g.dimz - 1) >> j) + 1;
+    if (warp == 0 && lane < 27) {  // point ranges of the 27 super-cells (Morton prefix ranges)
+      u32 pstart = 0, pend = 0;
+      int x = sx + (lane % 3) - 1, y = sy + ((lane / 3) % 3) - 1, z = sz + (lane / 9) - 1;
+      if (x >= 0 && x < sdx && y >= 0 && y < sdy && z >= 0 && z < sdz) {
+        u64 pfx = morton3((u32)x, (u32)y, (u32)z);
+        u64 klo = pfx << (3 * j), khi = (pfx + 1) << (3 * j);
+        u32 a = lower_bound_u64(g.cell_key, g.n_cells, klo);
+        u32 b = lower_bound_u64(g.cell_key, g.n_cells, khi);
+        pstart = g.cell_start[a];
+        pend = g.cell_start[b];
+      }
+      s_ps[lane] = pstart;
+      s_pe[lane] = pend;
+    }
+    __syncthreads();
+    best = KEY_MAX;
+    bsid = SID_NONE;
+    for (int c27 = warp; c27 < 27; c27 += 8) {
+      const u32 e = s_pe[c27];
+      for (u32 pi = s_ps[c27] + (u32)lane; pi < e; pi += 32u) {
+        const float4 P = spts[pi];
+        const u64 key = make_key(dist2_exact(Q.x, Q.y, Q.z, P.x, P.y, P.z), __float_as_uint(P.w));
+        if (key < best) {
+          best = key;
+          bsid = pi;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const u64 ok = __shfl_xor_sync(FULL, best, o);
+      const u32 os = __shfl_xor_sync(FULL, bsid, o);
+      if (ok < best) {
+        best = ok;
+        bsid = os;
+      }
+    }
+    if (lane == 0) {
+      s_key[warp] = best;
+      s_sid[warp] = bsid;
+    }
+    __syncthreads();
+    best = s_key[0];
+    bsid = s_sid[0];
+#pragma unroll
+    for (int w2 = 1; w2 < 8; ++w2)
+      if (s_key[w2] < best) {
+        best = s_key[w2];
+        bsid = s_sid[w2];
+      }
+    // distance from the query to the nearest unscanned cell (as in knn_general_kernel)
+    const double cs = g.cell * (double)(1 << j);
+    double bound = INFINITY;
+    {
+      int bx0 = max(sx - 1, 0), bx1 = min(sx + 1, sdx - 1);
+      int by0 = max(sy - 1, 0), by1 = min(sy + 1, sdy - 1);
+      int bz0 = max(sz - 1, 0), bz1 = min(sz + 1, sdz - 1);
+      if (bx0 > 0) bound = fmin(bound, fmax(0.0, ((double)Q.x - g.ox) - bx0 * cs));
+      if (bx1 < sdx - 1) bound = fmin(bound, fmax(0.0, (bx1 + 1) * cs - ((double)Q.x - g.ox)));
+      if (by0 > 0) bound = fmin(bound, fmax(0.0, ((double)Q.y - g.oy) - by0 * cs));
+      if (by1 < sdy - 1) bound = fmin(bound, fmax(0.0, (by1 + 1) * cs - ((double)Q.y - g.oy)));
+      if (bz0 > 0) bound = fmin(bound, fmax(0.0, ((double)Q.z - g.oz) - bz0 * cs));
+      if (bz1 < sdz - 1) bound = fmin(bound, fmax(0.0, (bz1 + 1) * cs - ((double)Q.z - g.oz)));
+    }
+    if (isinf(bound)) break;  // the block covers the whole grid
+    if (best != KEY_MAX) {
+      double b = bound * (1.0 - 1e-6);
+      float kd2 = __uint_as_float((u32)(best >> 32));
+      if (kd2 <= __double2float_rd(b * b)) break;
+    }
+    __syncthreads();  // every thread has read this stage's tables before the next stage rewrites them
+  }
+  if (threadIdx.x == 0) {
+    out_sid[it] = bsid;
+    if (out_d2) out_d2[it] = bsid == SID_NONE ? INFINITY : __uint_as_float((u32)(best >> 32));
+  }
+}
+
 // ---------------------------------------------------------------------------
 static size_t cell_kernel_smem(int E, int cap) {
   int CS = 32 * E;
@@ -731,6 +835,12 @@ int knn_query_run(iftwt_ctx* c, const float4* d_q, size_t m, int k, u32* d_idx_s
   if (k < 1 || k > 64) return ctx_fail(c, IFTWT_ERR_INVALID, "k must be in [1, 64], got %d", k);
   if (!c->grid_valid) TRY(grid_build(c, k < 8 ? 8 : k));
   if (m == 0) return IFTWT_OK;
+  if (k == 1 && m <= 2048 && !(getenv("IFTWT_NEAREST_BLOCK") && atoi(getenv("IFTWT_NEAREST_BLOCK")) == 0)) {
+    LAUNCH(c, knn_nearest_block_kernel, (unsigned)m, 256, 0, c->grid, (const float4*)c->spts.as<float4>(), d_q, (u32)m,
+           d_idx_sorted, d_d2);
+    CHECK_LAUNCH(c);
+    return IFTWT_OK;
+  }
   unsigned gblocks = (unsigned)((m + 7) / 8);
   if (gblocks > (unsigned)c->sm_count * 8) gblocks = c->sm_count * 8;
   {

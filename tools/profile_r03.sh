@@ -10,6 +10,7 @@ timeout 400 ncu --set full --clock-control none --import-source on -k regex:'knn
 python tools/ncu_raw_summary.py /tmp/prof_r03_top.ncu-rep "ncu --set full --clock-control none, bench.py cfg3 (10M facade, k=32), last step, end of round 2: k-NN fast path (both launches), general path, normals, region-growing classify (ballot form) + hook, segment sizes, reverse-arc fill, Morton gather" > $O/r03_top_kernels_ncu_full.txt
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 1800 --csv --log-file $O/r03_launches.csv $B > /tmp/ncu_a.log 2>&1
 python tools/ncu_launch_summary.py $O/r03_launches.csv $O/r03_launches.txt
+[ -n "$SKIP_IFT" ] && exit 0
 timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_requests_srcunit_tex_op_atom_dot_alu.sum,lts__t_requests_srcunit_tex_op_atom_dot_cas.sum,smsp__inst_executed.sum --clock-control none -k regex:ift_level_kernel --launch-skip 908 --launch-count 227 --csv --log-file /tmp/ift_levels_r03.csv $B > /tmp/ncu_c.log 2>&1
 python tools/ncu_ift_levels.py /tmp/ift_levels_r03.csv 227 $O/r03_ift_levels_ncu.txt
 tail -3 /tmp/ncu_a.log /tmp/ncu_b.log /tmp/ncu_c.log
