@@ -796,7 +796,7 @@ def main():
             pass
         roofline = {"bound": "hbm", "kernel": "knn_cell_kernel (first launch + the crowded-cell launch, one event pair)", "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic, "issue_slot": issue_slot,
-                    "active_limiter": "instruction issue (ncu: 79.2 % issue-active, ALU pipe 64 %, LSU pipe 56 %, DRAM 8.5 % busy), not HBM: "
+                    "active_limiter": "instruction issue (ncu: 78.4 % issue-active, ALU pipe 61 %, LSU pipe 53 %, DRAM 8.8 % busy), not HBM: "
                                       "see issue_slot",
                     "peak_source": which, "algorithmic_bytes_per_launch": alg_bytes,
                     "avg_launch_ms": knn_ms}
