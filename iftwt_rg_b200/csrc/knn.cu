@@ -9,16 +9,19 @@
 //
 // Fast path (knn_cell_kernel): one warp per occupied cell.  The warp looks the 27
 // cells of the 3x3x3 block up in the cell hash, stages their points in shared
-// memory with coalesced float4 loads, and then answers the cell's own queries one
-// by one: 32 lanes evaluate the staged candidates, a count-based threshold search
-// (ballot + popc, candidates ~ tau in 2-D) narrows them to at most CS survivors,
-// and the survivors are ranked against each other in shared memory — the rank IS
-// the output slot, so no sorting network and no shuffles are needed.  A query is
-// finished when its k-th distance is inside the block (per-point bound from
+// memory with coalesced float4 loads (32 slots per round, whatever cell they come
+// from), and then answers the cell's own queries one by one: 32 lanes evaluate the
+// staged candidates, a count-based threshold search (per-lane counts + one warp
+// reduction; candidates ~ tau in 2-D) narrows them to at most CS survivors, which
+// are compacted lane-major into shared memory and ordered — k <= 16 and k > 32: ranked
+// against each other, the rank IS the output slot; 17 <= k <= 32: a 64-key bitonic
+// network over packed (quantised d2, list position) keys, at most 48 of them real.  A
+// query is finished when its k-th distance is inside the block (per-point bound from
 // grid.cu); otherwise it is appended to the fallback list.
 //
 // General path (knn_general_kernel): one warp per query, for fallback queries and
-// for external query points.  Stage j scans the 3x3x3 block of super-cells of side
+// for external query points (a handful of k = 1 queries: one block per query,
+// knn_nearest_block_kernel).  Stage j scans the 3x3x3 block of super-cells of side
 // cell*2^j (contiguous Morton-prefix ranges of the sorted cloud, found by binary
 // search in the cell table), keeps the k best in a lane-distributed sorted list,
 // and stops when the k-th distance is inside the scanned block.

@@ -56,7 +56,11 @@ __device__ __forceinline__ u64 rg_key(const float4* __restrict__ nrm, const floa
 }
 // Region-growing arcs in two kernels.
 //
-// rg_classify_kernel — one warp per tile of 32 consecutive (Morton-adjacent) vertices, one lane
+// rg_classify_pow2_kernel — the form every BASELINE config runs (k = 16 / 32): as below, but a round of 32 entries
+// is the whole row of one vertex (or of two), so the masks of a vertex are ballots over its round and the vertex's
+// first parent is its hook neighbour with the smallest id (redux.min); see the kernel.
+//
+// rg_classify_kernel (any k) — one warp per tile of 32 consecutive (Morton-adjacent) vertices, one lane
 // per ENTRY (vertex, j) of the tile's 32 x k row block.  The 32 entries of a request are
 // consecutive in memory (coalesced index / distance loads) and are the neighbours of one or
 // two vertices, so the gathers of the neighbour's normal and k-th key fall on the few lines one
